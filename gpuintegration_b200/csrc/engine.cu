@@ -1,0 +1,1388 @@
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+
+#include "stages.cuh"
+
+namespace pgn {
+
+namespace {
+thread_local std::string g_last_error;
+
+#define PGN_CUDA(expr)                                                                             \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                         \
+      return _e == cudaErrorMemoryAllocation ? PGN_ERR_NOMEM : PGN_ERR_CUDA;                       \
+    }                                                                                              \
+  } while (0)
+
+#define PGN_TRY(expr)                                                                              \
+  do {                                                                                             \
+    int _rc = (expr);                                                                              \
+    if (_rc != PGN_OK)                                                                             \
+      return _rc;                                                                                  \
+  } while (0)
+
+constexpr int kHostStats = kStatsLen;
+
+// pack / unpack of the columns that travel with a region during a rebalance:
+// 2*ndim bounds columns, parent estimate, parent error, split axis (as a double)
+__global__ void
+k_pack(const double* __restrict__ left, const double* __restrict__ length,
+       const double* __restrict__ pest, const double* __restrict__ perr,
+       const int32_t* __restrict__ axis, size_t m, int ndim, size_t first, size_t count,
+       double* __restrict__ out)
+{
+  const size_t cols = 2 * static_cast<size_t>(ndim) + 3;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < cols * count;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t c = t / count, j = t - c * count, i = first + j;
+    double v;
+    if (c < static_cast<size_t>(ndim))
+      v = left[c * m + i];
+    else if (c < 2 * static_cast<size_t>(ndim))
+      v = length[(c - ndim) * m + i];
+    else if (c == 2 * static_cast<size_t>(ndim))
+      v = pest[i];
+    else if (c == 2 * static_cast<size_t>(ndim) + 1)
+      v = perr[i];
+    else
+      v = static_cast<double>(axis[i]);
+    out[t] = v;
+  }
+}
+
+__global__ void
+k_unpack(const double* __restrict__ in, size_t count, size_t first, size_t m_new, int ndim,
+         double* __restrict__ left, double* __restrict__ length, double* __restrict__ pest,
+         double* __restrict__ perr, int32_t* __restrict__ axis)
+{
+  const size_t cols = 2 * static_cast<size_t>(ndim) + 3;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < cols * count;
+       t += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t c = t / count, j = t - c * count, i = first + j;
+    const double v = in[t];
+    if (c < static_cast<size_t>(ndim))
+      left[c * m_new + i] = v;
+    else if (c < 2 * static_cast<size_t>(ndim))
+      length[(c - ndim) * m_new + i] = v;
+    else if (c == 2 * static_cast<size_t>(ndim))
+      pest[i] = v;
+    else if (c == 2 * static_cast<size_t>(ndim) + 1)
+      perr[i] = v;
+    else
+      axis[i] = static_cast<int32_t>(v);
+  }
+}
+
+unsigned
+blocks_for(size_t work, int block)
+{
+  size_t b = (work + block - 1) / block;
+  if (b < 1)
+    b = 1;
+  if (b > 148u * 32u)
+    b = 148u * 32u;
+  return static_cast<unsigned>(b);
+}
+
+}  // namespace
+
+void
+set_last_error(const std::string& msg)
+{
+  g_last_error = msg;
+}
+const char*
+last_error()
+{
+  return g_last_error.c_str();
+}
+
+// ------------------------------------------------------------------------------------------------
+int
+DeviceBuf::reserve(size_t need)
+{
+  if (need <= bytes)
+    return PGN_OK;
+  // grow with head-room: the region list can double every iteration
+  size_t want = need + need / 4;
+  if (want < 4096)
+    want = 4096;
+  if (ptr) {
+    cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+  cudaError_t e = cudaMalloc(&ptr, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    e = cudaMalloc(&ptr, need);
+    want = need;
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    ptr = nullptr;
+    set_last_error("device allocation of " + std::to_string(need) + " bytes failed");
+    return PGN_ERR_NOMEM;
+  }
+  bytes = want;
+  return PGN_OK;
+}
+
+void
+DeviceBuf::release()
+{
+  if (ptr)
+    cudaFree(ptr);
+  ptr = nullptr;
+  bytes = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+void
+ConvergenceTracker::reset(double rel, double abs_)
+{
+  epsrel = rel;
+  epsabs = abs_;
+  required_digits = static_cast<int>(std::ceil(std::log10(1 / epsrel)));
+  last[0] = last[1] = last[2] = 0.0;
+  collected = 0;
+}
+
+void
+ConvergenceTracker::store(double estimate)
+{
+  last[0] = last[1];
+  last[1] = last[2];
+  last[2] = estimate;
+  collected++;
+}
+
+// heuristic_classifier.cuh:169-203: the last three estimates, scaled up to >= 1, printed with 15
+// decimals, must share their first `required_digits` significant characters.
+bool
+ConvergenceTracker::sig_digits_same() const
+{
+  auto norm = [](double v) {
+    v = std::fabs(v);
+    while (v != 0. && v < 1.)
+      v *= 10;
+    return v;
+  };
+  auto fixed15 = [](double v) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%.15f", v);
+    return std::string(buf);
+  };
+  const std::string second_to_last = fixed15(norm(last[0]));
+  const std::string prev = fixed15(norm(last[1]));
+  const std::string current = fixed15(norm(last[2]));
+  auto at = [](const std::string& s, int i) {
+    return i < static_cast<int>(s.size()) ? s[i] : '\0';
+  };
+  bool verdict = true;
+  int sig = 0;
+  for (int i = 0; i < required_digits + 1 && sig < required_digits && verdict; ++i) {
+    verdict = at(current, i) == at(prev, i) && at(prev, i) == at(second_to_last, i);
+    sig += (verdict && at(current, i) != '.') ? 1 : 0;
+  }
+  return verdict;
+}
+
+bool
+ConvergenceTracker::converged() const
+{
+  // heuristic_classifier.cuh:205-216 (min_iters_for_convergence = 1, unsigned arithmetic)
+  if (collected - 1 < 1 || !sig_digits_same())
+    return false;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+Engine::Engine(int ndim, const pgn_opts& opts) : ndim_(ndim), opts_(opts)
+{
+  for (int d = 0; d <= PGN_MAX_NDIM; ++d) {
+    lows_[d] = 0.0;
+    ranges_[d] = 1.0;
+  }
+}
+
+Engine::~Engine()
+{
+  if (ready_) {
+    cudaSetDevice(device_);
+    cudaStreamSynchronize(stream_);
+  }
+  delete comm_;
+  DeviceBuf* all[] = {&d_codes_,   &d_weights_, &d_scale_,    &d_norm_,     &left_[0],    &left_[1],
+                      &length_[0], &length_[1], &est_,        &err_raw_,    &err_ref_,    &axis_,
+                      &active_,    &par_est_[0], &par_est_[1], &par_err_[0], &par_err_[1], &par_axis_,
+                      &partials_,  &tile_count_, &tile_offset_, &done_,      &stats_dev_,  &stats_glob_,
+                      &digest_dev_, &pack_send_, &pack_recv_};
+  for (DeviceBuf* b : all)
+    b->release();
+  if (host_local_)
+    cudaFreeHost(host_local_);
+  if (host_global_)
+    cudaFreeHost(host_global_);
+  for (cudaEvent_t& e : ev_)
+    if (e)
+      cudaEventDestroy(e);
+  if (stream_)
+    cudaStreamDestroy(stream_);
+}
+
+int
+Engine::init()
+{
+  if (!build_rule(ndim_, &rule_)) {
+    set_last_error("ndim must be in [2, 15]");
+    return PGN_ERR_INVALID;
+  }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    set_last_error("no CUDA device: pagani_b200 has no CPU fallback");
+    return PGN_ERR_NO_DEVICE;
+  }
+  if (opts_.device >= 0)
+    device_ = opts_.device;
+  else
+    PGN_CUDA(cudaGetDevice(&device_));
+  if (device_ >= count) {
+    set_last_error("device ordinal out of range");
+    return PGN_ERR_INVALID;
+  }
+  PGN_CUDA(cudaSetDevice(device_));
+  cudaDeviceProp prop;
+  PGN_CUDA(cudaGetDeviceProperties(&prop, device_));
+  if (prop.major < 10) {
+    set_last_error(std::string("device ") + prop.name +
+                   " is not sm_100 or newer: this build carries sm_100a code only");
+    return PGN_ERR_NO_DEVICE;
+  }
+  sm_count_ = prop.multiProcessorCount;
+  PGN_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  for (cudaEvent_t& e : ev_)
+    PGN_CUDA(cudaEventCreate(&e));
+
+  PGN_TRY(d_codes_.reserve(sizeof(uint64_t) * rule_.feval));
+  PGN_TRY(d_weights_.reserve(sizeof(double) * kSets * kRules));
+  PGN_TRY(d_scale_.reserve(sizeof(double) * kSets * kRules));
+  PGN_TRY(d_norm_.reserve(sizeof(double) * kSets * kRules));
+  PGN_CUDA(cudaMemcpy(d_codes_.ptr, rule_.point_code.data(), sizeof(uint64_t) * rule_.feval,
+                      cudaMemcpyHostToDevice));
+  PGN_CUDA(cudaMemcpy(d_weights_.ptr, rule_.weights, sizeof(double) * kSets * kRules,
+                      cudaMemcpyHostToDevice));
+  PGN_CUDA(cudaMemcpy(d_scale_.ptr, rule_.scale, sizeof(double) * kSets * kRules,
+                      cudaMemcpyHostToDevice));
+  PGN_CUDA(cudaMemcpy(d_norm_.ptr, rule_.norm, sizeof(double) * kSets * kRules,
+                      cudaMemcpyHostToDevice));
+
+  PGN_TRY(done_.reserve(sizeof(unsigned int)));
+  PGN_CUDA(cudaMemset(done_.ptr, 0, sizeof(unsigned int)));
+  PGN_TRY(stats_dev_.reserve(sizeof(double) * kStatsLen));
+  PGN_TRY(stats_glob_.reserve(sizeof(double) * kStatsLen));
+  PGN_TRY(digest_dev_.reserve(sizeof(unsigned long long) * 8));
+  PGN_CUDA(cudaMallocHost(&host_local_, sizeof(double) * kHostStats));
+  PGN_CUDA(cudaMallocHost(&host_global_, sizeof(double) * kHostStats));
+  rank_counts_.assign(1, 0);
+  ready_ = true;
+  return PGN_OK;
+}
+
+int
+Engine::rule_view(pgn_rule_view* out) const
+{
+  if (!out)
+    return PGN_ERR_INVALID;
+  out->ndim = ndim_;
+  out->feval = rule_.feval;
+  out->point_code = d_codes_.as<uint64_t>();
+  out->weights = d_weights_.as<double>();
+  out->scale = d_scale_.as<double>();
+  out->norm = d_norm_.as<double>();
+  for (int c = 0; c < kCodes; ++c) {
+    out->half_plus_g[c] = rule_.half_plus_g[c];
+    out->half_minus_g[c] = rule_.half_minus_g[c];
+  }
+  out->ratio = rule_.ratio;
+  out->two_one_minus_ratio_unused = 0.0;
+  return PGN_OK;
+}
+
+int
+Engine::device_info(int* sm_count, size_t* free_b, size_t* total_b)
+{
+  PGN_CUDA(cudaSetDevice(device_));
+  size_t f = 0, t = 0;
+  PGN_CUDA(cudaMemGetInfo(&f, &t));
+  if (sm_count)
+    *sm_count = sm_count_;
+  if (free_b)
+    *free_b = f;
+  if (total_b)
+    *total_b = t;
+  return PGN_OK;
+}
+
+int
+Engine::set_volume(const double* lows, const double* highs)
+{
+  // PaganiUtils.cuh:98-112 + the per-block prologue of INIT_REGION_POOL (Phases.cuh:338-343):
+  // ranges and their running product (the Jacobian) are launch constants, computed here once.
+  double jac = 1.0;
+  for (int d = 0; d < ndim_; ++d) {
+    const double lo = lows ? lows[d] : 0.0;
+    const double hi = highs ? highs[d] : 1.0;
+    lows_[d] = lo;
+    ranges_[d] = hi - lo;
+    jac = jac * ranges_[d];
+  }
+  jacobian_ = jac;
+  return PGN_OK;
+}
+
+int
+Engine::tiles_for(size_t n) const
+{
+  return static_cast<int>((n + kTile - 1) / kTile);
+}
+
+int
+Engine::ensure_iteration_buffers(size_t n)
+{
+  const size_t nn = n > 0 ? n : 1;
+  PGN_TRY(est_.reserve(sizeof(double) * nn));
+  PGN_TRY(err_raw_.reserve(sizeof(double) * nn));
+  PGN_TRY(err_ref_.reserve(sizeof(double) * nn));
+  PGN_TRY(axis_.reserve(sizeof(int32_t) * nn));
+  PGN_TRY(active_.reserve(nn));
+  const size_t tiles = static_cast<size_t>(tiles_for(nn));
+  PGN_TRY(partials_.reserve(sizeof(double) * kStatCount * tiles));
+  PGN_TRY(tile_count_.reserve(sizeof(uint32_t) * tiles));
+  PGN_TRY(tile_offset_.reserve(sizeof(uint64_t) * tiles));
+  return PGN_OK;
+}
+
+int
+Engine::regions_init_uniform(int parts)
+{
+  if (parts < 1)
+    return PGN_ERR_INVALID;
+  PGN_CUDA(cudaSetDevice(device_));
+  // Sub_regions::uniform_split (Sub_regions.cuh:164-185); with several ranks every rank builds its
+  // contiguous slice of the global grid.
+  double total_d = 1.0;
+  for (int d = 0; d < ndim_; ++d)
+    total_d *= parts;
+  if (total_d > 4e9) {
+    set_last_error("initial grid too large");
+    return PGN_ERR_INVALID;
+  }
+  const size_t total = static_cast<size_t>(total_d + 0.5);
+  const int w = comm_ ? comm_->nranks : 1, r = comm_ ? comm_->rank : 0;
+  const size_t lo = total * r / w, hi = total * (r + 1) / w;
+  const size_t n = hi - lo;
+  const double edge = 1. / static_cast<double>(parts);
+  PGN_TRY(left_[cur_].reserve(sizeof(double) * std::max<size_t>(n, 1) * ndim_));
+  PGN_TRY(length_[cur_].reserve(sizeof(double) * std::max<size_t>(n, 1) * ndim_));
+  if (w == 1) {
+    if (n > 0)
+      k_uniform_split<<<blocks_for(n, 512), 512, 0, stream_>>>(
+        left_[cur_].as<double>(), length_[cur_].as<double>(), n, parts, ndim_, edge);
+    PGN_CUDA(cudaGetLastError());
+  } else {
+    // small: build the slice on the host with the same arithmetic
+    std::vector<double> hl(n * ndim_), hw(n * ndim_);
+    for (size_t t = lo; t < hi; ++t) {
+      size_t q = t;
+      for (int d = 0; d < ndim_; ++d) {
+        const size_t id = q % parts;
+        q /= parts;
+        hl[static_cast<size_t>(d) * n + (t - lo)] = static_cast<double>(id) * edge;
+        hw[static_cast<size_t>(d) * n + (t - lo)] = edge;
+      }
+    }
+    if (n > 0) {
+      PGN_CUDA(cudaMemcpyAsync(left_[cur_].ptr, hl.data(), sizeof(double) * hl.size(),
+                               cudaMemcpyHostToDevice, stream_));
+      PGN_CUDA(cudaMemcpyAsync(length_[cur_].ptr, hw.data(), sizeof(double) * hw.size(),
+                               cudaMemcpyHostToDevice, stream_));
+      PGN_CUDA(cudaStreamSynchronize(stream_));
+    }
+  }
+  n_ = n;
+  parents_n_ = 0;
+  evaluated_ = classified_ = filtered_pending_ = false;
+  return PGN_OK;
+}
+
+int
+Engine::regions_import(const double* left, const double* length, size_t n)
+{
+  if ((!left || !length) && n > 0)
+    return PGN_ERR_INVALID;
+  PGN_CUDA(cudaSetDevice(device_));
+  PGN_TRY(left_[cur_].reserve(sizeof(double) * std::max<size_t>(n, 1) * ndim_));
+  PGN_TRY(length_[cur_].reserve(sizeof(double) * std::max<size_t>(n, 1) * ndim_));
+  if (n > 0) {
+    PGN_CUDA(cudaMemcpyAsync(left_[cur_].ptr, left, sizeof(double) * n * ndim_,
+                             cudaMemcpyHostToDevice, stream_));
+    PGN_CUDA(cudaMemcpyAsync(length_[cur_].ptr, length, sizeof(double) * n * ndim_,
+                             cudaMemcpyHostToDevice, stream_));
+    PGN_CUDA(cudaStreamSynchronize(stream_));
+  }
+  n_ = n;
+  parents_n_ = 0;
+  evaluated_ = classified_ = filtered_pending_ = false;
+  return PGN_OK;
+}
+
+int
+Engine::regions_export(double* left, double* length, size_t cap, size_t* n)
+{
+  if (n)
+    *n = n_;
+  if (cap < n_)
+    return left || length ? PGN_ERR_INVALID : PGN_OK;
+  PGN_CUDA(cudaSetDevice(device_));
+  if (n_ > 0 && left)
+    PGN_CUDA(cudaMemcpyAsync(left, left_[cur_].ptr, sizeof(double) * n_ * ndim_,
+                             cudaMemcpyDeviceToHost, stream_));
+  if (n_ > 0 && length)
+    PGN_CUDA(cudaMemcpyAsync(length, length_[cur_].ptr, sizeof(double) * n_ * ndim_,
+                             cudaMemcpyDeviceToHost, stream_));
+  PGN_CUDA(cudaStreamSynchronize(stream_));
+  return PGN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int
+Engine::launch_evaluate(pgn_eval_fn fn, void* user)
+{
+  PGN_TRY(ensure_iteration_buffers(n_));
+  if (n_ == 0)
+    return PGN_OK;
+  pgn_region_view v;
+  std::memset(&v, 0, sizeof v);
+  v.left = left_[cur_].as<double>();
+  v.length = length_[cur_].as<double>();
+  v.n = n_;
+  v.estimate = est_.as<double>();
+  v.errorest = err_raw_.as<double>();
+  v.axis = axis_.as<int32_t>();
+  for (int d = 0; d <= PGN_MAX_NDIM; ++d) {
+    v.lows[d] = lows_[d];
+    v.ranges[d] = ranges_[d];
+  }
+  v.jacobian = jacobian_;
+  rule_view(&v.rule);
+  v.stream = stream_;
+  v.sm_count = sm_count_;
+  const int rc = fn(user, &v);
+  if (rc != PGN_OK) {
+    cudaError_t e = cudaGetLastError();
+    set_last_error(std::string("evaluation launch failed: ") + cudaGetErrorString(e));
+  }
+  return rc;
+}
+
+int
+Engine::sync_stats(bool need_minmax)
+{
+  const bool multi = comm_ && comm_->nranks > 1;
+  if (multi) {
+    PGN_CUDA(cudaMemcpyAsync(stats_glob_.ptr, stats_dev_.ptr, sizeof(double) * kStatsLen,
+                             cudaMemcpyDeviceToDevice, stream_));
+    PGN_TRY(comm_->allreduce(stats_glob_.as<double>(), kStatsLen, kOpSum, stream_));
+    if (need_minmax) {
+      PGN_CUDA(cudaMemcpyAsync(stats_glob_.as<double>() + kNegMinSlot,
+                               stats_dev_.as<double>() + kNegMinSlot, sizeof(double) * 2,
+                               cudaMemcpyDeviceToDevice, stream_));
+      PGN_TRY(comm_->allreduce(stats_glob_.as<double>() + kNegMinSlot, 2, kOpMax, stream_));
+    }
+    PGN_CUDA(cudaMemcpyAsync(host_global_, stats_glob_.ptr, sizeof(double) * kStatsLen,
+                             cudaMemcpyDeviceToHost, stream_));
+  }
+  PGN_CUDA(cudaMemcpyAsync(host_local_, stats_dev_.ptr, sizeof(double) * kStatsLen,
+                           cudaMemcpyDeviceToHost, stream_));
+  PGN_CUDA(cudaStreamSynchronize(stream_));
+  if (!multi)
+    std::memcpy(host_global_, host_local_, sizeof(double) * kStatsLen);
+  else if (!need_minmax) {
+    host_global_[kNegMinSlot] = std::numeric_limits<double>::quiet_NaN();
+    host_global_[kMaxSlot] = std::numeric_limits<double>::quiet_NaN();
+  }
+  const int w = comm_ ? comm_->nranks : 1;
+  rank_counts_.resize(w);
+  for (int r = 0; r < w; ++r)
+    rank_counts_[r] = static_cast<size_t>(host_global_[kRankSlot + r]);
+  return PGN_OK;
+}
+
+namespace {
+// statistics of an empty local list (a rank that ran out of regions still joins the collectives)
+int
+write_empty_stats(double* dev, cudaStream_t s)
+{
+  double h[kStatsLen];
+  for (int i = 0; i < kStatsLen; ++i)
+    h[i] = 0.0;
+  h[kMinErr] = std::numeric_limits<double>::infinity();
+  h[kMaxErr] = -std::numeric_limits<double>::infinity();
+  h[kNegMinSlot] = -std::numeric_limits<double>::infinity();
+  h[kMaxSlot] = -std::numeric_limits<double>::infinity();
+  // pageable source: the copy is staged before the call returns
+  return cudaMemcpyAsync(dev, h, sizeof h, cudaMemcpyHostToDevice, s) == cudaSuccess ? PGN_OK
+                                                                                       : PGN_ERR_CUDA;
+}
+}  // namespace
+
+int
+Engine::run_classify(double epsrel, int relerr)
+{
+  TileScratch ts{partials_.as<double>(), tile_count_.as<uint32_t>(), tile_offset_.as<uint64_t>(),
+                 done_.as<unsigned int>(), stats_dev_.as<double>(), comm_ ? comm_->rank : 0,
+                 comm_ ? comm_->nranks : 1};
+  if (n_ == 0) {
+    PGN_TRY(write_empty_stats(stats_dev_.as<double>(), stream_));
+    err_cur_ = err_raw_.as<double>();
+  } else if (parents_n_ > 0) {
+    k_classify<true><<<tiles_for(n_), kBlock, 0, stream_>>>(
+      est_.as<double>(), err_raw_.as<double>(), par_est_[par_cur_].as<double>(),
+      err_ref_.as<double>(), active_.as<uint8_t>(), n_, epsrel, relerr, ts);
+    err_cur_ = err_ref_.as<double>();
+  } else {
+    k_classify<false><<<tiles_for(n_), kBlock, 0, stream_>>>(
+      est_.as<double>(), err_raw_.as<double>(), nullptr, nullptr, active_.as<uint8_t>(), n_, epsrel,
+      relerr, ts);
+    err_cur_ = err_raw_.as<double>();
+  }
+  PGN_CUDA(cudaGetLastError());
+  classified_ = true;
+  return PGN_OK;
+}
+
+int
+Engine::run_threshold(int mode, double threshold)
+{
+  TileScratch ts{partials_.as<double>(), tile_count_.as<uint32_t>(), tile_offset_.as<uint64_t>(),
+                 done_.as<unsigned int>(), stats_dev_.as<double>(), comm_ ? comm_->rank : 0,
+                 comm_ ? comm_->nranks : 1};
+  if (n_ == 0)
+    return write_empty_stats(stats_dev_.as<double>(), stream_);
+  const int tiles = tiles_for(n_);
+  if (mode == 0)
+    k_threshold<0><<<tiles, kBlock, 0, stream_>>>(est_.as<double>(), err_cur_, active_.as<uint8_t>(),
+                                                  n_, threshold, ts);
+  else if (mode == 1)
+    k_threshold<1><<<tiles, kBlock, 0, stream_>>>(est_.as<double>(), err_cur_, active_.as<uint8_t>(),
+                                                  n_, threshold, ts);
+  else
+    k_threshold<2><<<tiles, kBlock, 0, stream_>>>(est_.as<double>(), err_cur_, active_.as<uint8_t>(),
+                                                  n_, threshold, ts);
+  PGN_CUDA(cudaGetLastError());
+  return PGN_OK;
+}
+
+int
+Engine::run_recount()
+{
+  TileScratch ts{partials_.as<double>(), tile_count_.as<uint32_t>(), tile_offset_.as<uint64_t>(),
+                 done_.as<unsigned int>(), stats_dev_.as<double>(), comm_ ? comm_->rank : 0,
+                 comm_ ? comm_->nranks : 1};
+  if (n_ == 0)
+    return write_empty_stats(stats_dev_.as<double>(), stream_);
+  k_recount<<<tiles_for(n_), kBlock, 0, stream_>>>(est_.as<double>(), err_cur_,
+                                                   active_.as<uint8_t>(), n_, ts);
+  PGN_CUDA(cudaGetLastError());
+  return PGN_OK;
+}
+
+uint64_t
+Engine::digest_device(const void* p, size_t elem, size_t n)
+{
+  unsigned long long* out = digest_dev_.as<unsigned long long>();
+  cudaMemsetAsync(out, 0, sizeof(unsigned long long), stream_);
+  if (n > 0) {
+    const unsigned g = blocks_for(n, 256);
+    if (elem == 8)
+      k_digest<double><<<g, 256, 0, stream_>>>(static_cast<const double*>(p), n, out);
+    else if (elem == 4)
+      k_digest<int32_t><<<g, 256, 0, stream_>>>(static_cast<const int32_t*>(p), n, out);
+    else
+      k_digest<uint8_t><<<g, 256, 0, stream_>>>(static_cast<const uint8_t*>(p), n, out);
+  }
+  unsigned long long h = 0;
+  cudaMemcpyAsync(&h, out, sizeof h, cudaMemcpyDeviceToHost, stream_);
+  cudaStreamSynchronize(stream_);
+  return h;
+}
+
+void
+Engine::digest_arrays(pgn_iter_stats* st, bool after_classify)
+{
+  if (!after_classify) {
+    st->dig_left = digest_device(left_[cur_].ptr, 8, n_ * ndim_);
+    st->dig_length = digest_device(length_[cur_].ptr, 8, n_ * ndim_);
+    st->dig_estimate = digest_device(est_.ptr, 8, n_);
+    st->dig_errorest_raw = digest_device(err_raw_.ptr, 8, n_);
+    st->dig_axis = digest_device(axis_.ptr, 4, n_);
+  } else {
+    st->dig_errorest = digest_device(err_cur_, 8, n_);
+    st->dig_active = digest_device(active_.ptr, 1, n_);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage-level API
+// ------------------------------------------------------------------------------------------------
+int
+Engine::evaluate(pgn_eval_fn fn, void* user, double* sum_est, double* sum_err)
+{
+  if (!fn)
+    return PGN_ERR_INVALID;
+  PGN_CUDA(cudaSetDevice(device_));
+  if (filtered_pending_) {
+    set_last_error("evaluate() between filter() and split()");
+    return PGN_ERR_STATE;
+  }
+  PGN_TRY(launch_evaluate(fn, user));
+  evaluated_ = true;
+  // apply_cubature_integration_rules also resets every flag to active and returns the two sums
+  // (PaganiUtils.cuh:310-311, 336-341); parents are left untouched.
+  const size_t keep_parents = parents_n_;
+  parents_n_ = 0;
+  int rc = run_classify(0.0, 0);
+  parents_n_ = keep_parents;
+  PGN_TRY(rc);
+  classified_ = false;
+  PGN_TRY(sync_stats(false));
+  if (sum_est)
+    *sum_est = host_global_[kSumEst];
+  if (sum_err)
+    *sum_err = host_global_[kSumErr];
+  return PGN_OK;
+}
+
+int
+Engine::classify(double epsrel, int relerr, pgn_iter_stats* out)
+{
+  PGN_CUDA(cudaSetDevice(device_));
+  if (!evaluated_) {
+    set_last_error("classify() before evaluate()");
+    return PGN_ERR_STATE;
+  }
+  PGN_TRY(run_classify(epsrel, relerr));
+  PGN_TRY(sync_stats(false));
+  if (out) {
+    std::memset(out, 0, sizeof *out);
+    out->nregions = n_;
+    size_t ng = 0;
+    out->iter_estimate = host_global_[kSumEst];
+    out->iter_errorest = host_global_[kSumErr];
+    out->finished_estimate = host_global_[kSumEst] - host_global_[kSumActEst];
+    out->finished_errorest = host_global_[kSumErr] - host_global_[kSumActErr];
+    out->nactive = static_cast<uint64_t>(host_global_[kNumActive]);
+    (void)ng;
+  }
+  return PGN_OK;
+}
+
+int
+Engine::set_active(const uint8_t* flags, size_t n)
+{
+  if (n != n_ || (!flags && n > 0))
+    return PGN_ERR_INVALID;
+  PGN_CUDA(cudaSetDevice(device_));
+  PGN_TRY(ensure_iteration_buffers(n_));
+  if (!err_cur_)
+    err_cur_ = err_raw_.as<double>();
+  if (n > 0)
+    PGN_CUDA(cudaMemcpyAsync(active_.ptr, flags, n, cudaMemcpyHostToDevice, stream_));
+  PGN_TRY(run_recount());
+  PGN_TRY(sync_stats(false));
+  classified_ = true;
+  return PGN_OK;
+}
+
+int
+Engine::set_estimates(const double* est, const double* err, const int32_t* axis, size_t n)
+{
+  if (n != n_)
+    return PGN_ERR_INVALID;
+  PGN_CUDA(cudaSetDevice(device_));
+  PGN_TRY(ensure_iteration_buffers(n_));
+  if (n > 0) {
+    if (est)
+      PGN_CUDA(cudaMemcpyAsync(est_.ptr, est, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));
+    if (err)
+      PGN_CUDA(
+        cudaMemcpyAsync(err_raw_.ptr, err, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));
+    if (axis)
+      PGN_CUDA(
+        cudaMemcpyAsync(axis_.ptr, axis, sizeof(int32_t) * n, cudaMemcpyHostToDevice, stream_));
+  }
+  PGN_CUDA(cudaStreamSynchronize(stream_));
+  err_cur_ = err_raw_.as<double>();
+  evaluated_ = true;
+  return PGN_OK;
+}
+
+int
+Engine::fetch_estimates(double* est, double* err, int32_t* axis, uint8_t* active, size_t cap)
+{
+  if (cap < n_)
+    return PGN_ERR_INVALID;
+  PGN_CUDA(cudaSetDevice(device_));
+  if (n_ > 0) {
+    if (est)
+      PGN_CUDA(cudaMemcpyAsync(est, est_.ptr, sizeof(double) * n_, cudaMemcpyDeviceToHost, stream_));
+    if (err)
+      PGN_CUDA(cudaMemcpyAsync(err, err_cur_ ? err_cur_ : err_raw_.as<double>(), sizeof(double) * n_,
+                               cudaMemcpyDeviceToHost, stream_));
+    if (axis)
+      PGN_CUDA(
+        cudaMemcpyAsync(axis, axis_.ptr, sizeof(int32_t) * n_, cudaMemcpyDeviceToHost, stream_));
+    if (active)
+      PGN_CUDA(cudaMemcpyAsync(active, active_.ptr, n_, cudaMemcpyDeviceToHost, stream_));
+  }
+  PGN_CUDA(cudaStreamSynchronize(stream_));
+  return PGN_OK;
+}
+
+int
+Engine::fetch_parents(double* est, double* err, int32_t* axis, size_t cap, size_t* n)
+{
+  if (n)
+    *n = parents_n_;
+  if (cap < parents_n_)
+    return (est || err || axis) ? PGN_ERR_INVALID : PGN_OK;
+  PGN_CUDA(cudaSetDevice(device_));
+  if (parents_n_ > 0) {
+    if (est)
+      PGN_CUDA(cudaMemcpyAsync(est, par_est_[par_cur_].ptr, sizeof(double) * parents_n_,
+                               cudaMemcpyDeviceToHost, stream_));
+    if (err)
+      PGN_CUDA(cudaMemcpyAsync(err, par_err_[par_cur_].ptr, sizeof(double) * parents_n_,
+                               cudaMemcpyDeviceToHost, stream_));
+    if (axis && filtered_pending_)
+      PGN_CUDA(cudaMemcpyAsync(axis, par_axis_.ptr, sizeof(int32_t) * parents_n_,
+                               cudaMemcpyDeviceToHost, stream_));
+  }
+  PGN_CUDA(cudaStreamSynchronize(stream_));
+  return PGN_OK;
+}
+
+// Sub_regions_filter::filter (Sub_region_filter.cuh:85-139): compaction only.
+int
+Engine::filter(size_t* num_active)
+{
+  PGN_CUDA(cudaSetDevice(device_));
+  if (!classified_) {
+    set_last_error("filter() needs classify() or set_active() first");
+    return PGN_ERR_STATE;
+  }
+  const size_t m = static_cast<size_t>(host_local_[kNumActive]);
+  if (num_active)
+    *num_active = m;
+  if (m == 0) {
+    // the reference returns early and leaves the list untouched; the caller sets size = 0
+    n_ = 0;
+    parents_n_ = 0;
+    evaluated_ = classified_ = false;
+    return PGN_OK;
+  }
+  const int nxt = 1 - cur_, pn = 1 - par_cur_;
+  PGN_TRY(left_[nxt].reserve(sizeof(double) * m * ndim_));
+  PGN_TRY(length_[nxt].reserve(sizeof(double) * m * ndim_));
+  PGN_TRY(par_est_[pn].reserve(sizeof(double) * m));
+  PGN_TRY(par_err_[pn].reserve(sizeof(double) * m));
+  PGN_TRY(par_axis_.reserve(sizeof(int32_t) * m));
+  CompactArgs A;
+  A.left = left_[cur_].as<double>();
+  A.length = length_[cur_].as<double>();
+  A.est = est_.as<double>();
+  A.err = err_cur_;
+  A.axis = axis_.as<int32_t>();
+  A.active = active_.as<uint8_t>();
+  A.tile_offset = tile_offset_.as<uint64_t>();
+  A.n = n_;
+  A.m = m;
+  A.out_left = left_[nxt].as<double>();
+  A.out_length = length_[nxt].as<double>();
+  A.parent_est = par_est_[pn].as<double>();
+  A.parent_err = par_err_[pn].as<double>();
+  A.out_axis = par_axis_.as<int32_t>();
+  A.ndim = ndim_;
+  k_compact<false><<<tiles_for(n_), kBlock, 0, stream_>>>(A);
+  PGN_CUDA(cudaGetLastError());
+  cur_ = nxt;
+  par_cur_ = pn;
+  n_ = m;
+  parents_n_ = m;
+  filtered_pending_ = true;
+  evaluated_ = classified_ = false;
+  return PGN_OK;
+}
+
+// Sub_region_splitter::split (Sub_region_splitter.cuh:55-87)
+int
+Engine::split()
+{
+  PGN_CUDA(cudaSetDevice(device_));
+  if (n_ == 0)
+    return PGN_OK;
+  if (!filtered_pending_) {
+    set_last_error("split() needs filter() first (it consumes the compacted split axes)");
+    return PGN_ERR_STATE;
+  }
+  const size_t m = n_;
+  const int nxt = 1 - cur_;
+  PGN_TRY(left_[nxt].reserve(sizeof(double) * 2 * m * ndim_));
+  PGN_TRY(length_[nxt].reserve(sizeof(double) * 2 * m * ndim_));
+  k_split<<<blocks_for(m, kBlock), kBlock, 0, stream_>>>(
+    left_[cur_].as<double>(), length_[cur_].as<double>(), par_axis_.as<int32_t>(), m, ndim_,
+    left_[nxt].as<double>(), length_[nxt].as<double>());
+  PGN_CUDA(cudaGetLastError());
+  cur_ = nxt;
+  n_ = 2 * m;
+  filtered_pending_ = false;
+  return PGN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU: move contiguous runs of compacted parents so every rank holds ~the same number
+// ------------------------------------------------------------------------------------------------
+int
+Engine::rebalance_parents(size_t* m_local)
+{
+  std::vector<size_t> new_counts;
+  std::vector<Transfer> plan;
+  plan_rebalance(rank_counts_, &new_counts, &plan);
+  const int me = comm_->rank;
+  const size_t m_old = *m_local, m_new = new_counts[me];
+  const size_t cols = 2 * static_cast<size_t>(ndim_) + 3;
+  // staging offsets (in doubles) of every transfer that touches this rank
+  std::vector<size_t> soff(plan.size(), 0), roff(plan.size(), 0);
+  size_t stot = 0, rtot = 0;
+  for (size_t k = 0; k < plan.size(); ++k) {
+    if (plan[k].src == me) {
+      soff[k] = stot;
+      stot += plan[k].count * cols;
+    }
+    if (plan[k].dst == me) {
+      roff[k] = rtot;
+      rtot += plan[k].count * cols;
+    }
+  }
+  PGN_TRY(pack_send_.reserve(sizeof(double) * std::max<size_t>(stot, 1)));
+  PGN_TRY(pack_recv_.reserve(sizeof(double) * std::max<size_t>(rtot, 1)));
+  const int pc = par_cur_;
+  for (size_t k = 0; k < plan.size(); ++k) {
+    const Transfer& t = plan[k];
+    if (t.src != me)
+      continue;
+    // self transfers are packed straight into the receive staging area
+    double* dst = t.dst == me ? pack_recv_.as<double>() + roff[k] : pack_send_.as<double>() + soff[k];
+    k_pack<<<blocks_for(t.count * cols, 256), 256, 0, stream_>>>(
+      left_[cur_].as<double>(), length_[cur_].as<double>(), par_est_[pc].as<double>(),
+      par_err_[pc].as<double>(), par_axis_.as<int32_t>(), m_old, ndim_, t.src_offset, t.count, dst);
+  }
+  PGN_CUDA(cudaGetLastError());
+  PGN_TRY(comm_->exchange(plan, pack_send_.as<double>(), soff, pack_recv_.as<double>(), roff, cols,
+                          stream_));
+  // unpack into the other buffers (the pre-compaction list is dead by now)
+  const int nxt = 1 - cur_, pn = 1 - par_cur_;
+  PGN_TRY(left_[nxt].reserve(sizeof(double) * std::max<size_t>(m_new, 1) * ndim_));
+  PGN_TRY(length_[nxt].reserve(sizeof(double) * std::max<size_t>(m_new, 1) * ndim_));
+  PGN_TRY(par_est_[pn].reserve(sizeof(double) * std::max<size_t>(m_new, 1)));
+  PGN_TRY(par_err_[pn].reserve(sizeof(double) * std::max<size_t>(m_new, 1)));
+  // the split axes are unpacked in place: every byte of par_axis_ was packed already
+  PGN_CUDA(cudaStreamSynchronize(stream_));
+  DeviceBuf new_axis;
+  PGN_TRY(new_axis.reserve(sizeof(int32_t) * std::max<size_t>(m_new, 1)));
+  for (size_t k = 0; k < plan.size(); ++k) {
+    const Transfer& t = plan[k];
+    if (t.dst != me)
+      continue;
+    k_unpack<<<blocks_for(t.count * cols, 256), 256, 0, stream_>>>(
+      pack_recv_.as<double>() + roff[k], t.count, t.dst_offset, m_new, ndim_,
+      left_[nxt].as<double>(), length_[nxt].as<double>(), par_est_[pn].as<double>(),
+      par_err_[pn].as<double>(), new_axis.as<int32_t>());
+  }
+  PGN_CUDA(cudaGetLastError());
+  PGN_CUDA(cudaStreamSynchronize(stream_));
+  par_axis_.release();
+  par_axis_ = new_axis;
+  cur_ = nxt;
+  par_cur_ = pn;
+  *m_local = m_new;
+  rank_counts_ = new_counts;
+  return PGN_OK;
+}
+
+int
+Engine::compact_and_split(size_t m_local, size_t m_global, bool* rebalanced)
+{
+  *rebalanced = false;
+  bool want_rebalance = false;
+  if (comm_ && comm_->nranks > 1 && m_global >= rebalance_min_) {
+    size_t mx = 0;
+    for (size_t c : rank_counts_)
+      mx = std::max(mx, c);
+    const double mean = static_cast<double>(m_global) / comm_->nranks;
+    want_rebalance = static_cast<double>(mx) > rebalance_ratio_ * mean;
+  }
+  CompactArgs A;
+  A.left = left_[cur_].as<double>();
+  A.length = length_[cur_].as<double>();
+  A.est = est_.as<double>();
+  A.err = err_cur_;
+  A.axis = axis_.as<int32_t>();
+  A.active = active_.as<uint8_t>();
+  A.tile_offset = tile_offset_.as<uint64_t>();
+  A.n = n_;
+  A.m = m_local;
+  A.ndim = ndim_;
+  const int nxt = 1 - cur_, pn = 1 - par_cur_;
+  const size_t m1 = std::max<size_t>(m_local, 1);
+  PGN_TRY(par_est_[pn].reserve(sizeof(double) * m1));
+  PGN_TRY(par_err_[pn].reserve(sizeof(double) * m1));
+  A.parent_est = par_est_[pn].as<double>();
+  A.parent_err = par_err_[pn].as<double>();
+  if (!want_rebalance) {
+    PGN_TRY(left_[nxt].reserve(sizeof(double) * 2 * m1 * ndim_));
+    PGN_TRY(length_[nxt].reserve(sizeof(double) * 2 * m1 * ndim_));
+    A.out_left = left_[nxt].as<double>();
+    A.out_length = length_[nxt].as<double>();
+    A.out_axis = nullptr;
+    if (n_ > 0 && m_local > 0)
+      k_compact<true><<<tiles_for(n_), kBlock, 0, stream_>>>(A);
+    PGN_CUDA(cudaGetLastError());
+    cur_ = nxt;
+    par_cur_ = pn;
+    n_ = 2 * m_local;
+    parents_n_ = m_local;
+    return PGN_OK;
+  }
+  // compaction only, exchange, then bisect
+  PGN_TRY(left_[nxt].reserve(sizeof(double) * m1 * ndim_));
+  PGN_TRY(length_[nxt].reserve(sizeof(double) * m1 * ndim_));
+  PGN_TRY(par_axis_.reserve(sizeof(int32_t) * m1));
+  A.out_left = left_[nxt].as<double>();
+  A.out_length = length_[nxt].as<double>();
+  A.out_axis = par_axis_.as<int32_t>();
+  if (n_ > 0 && m_local > 0)
+    k_compact<false><<<tiles_for(n_), kBlock, 0, stream_>>>(A);
+  PGN_CUDA(cudaGetLastError());
+  cur_ = nxt;
+  par_cur_ = pn;
+  size_t m = m_local;
+  PGN_TRY(rebalance_parents(&m));
+  *rebalanced = true;
+  const int nx2 = 1 - cur_;
+  const size_t m2 = std::max<size_t>(m, 1);
+  PGN_TRY(left_[nx2].reserve(sizeof(double) * 2 * m2 * ndim_));
+  PGN_TRY(length_[nx2].reserve(sizeof(double) * 2 * m2 * ndim_));
+  if (m > 0)
+    k_split<<<blocks_for(m, kBlock), kBlock, 0, stream_>>>(
+      left_[cur_].as<double>(), length_[cur_].as<double>(), par_axis_.as<int32_t>(), m, ndim_,
+      left_[nx2].as<double>(), length_[nx2].as<double>());
+  PGN_CUDA(cudaGetLastError());
+  cur_ = nx2;
+  n_ = 2 * m;
+  parents_n_ = m;
+  return PGN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// heuristic (memory-pressure) classifier
+// ------------------------------------------------------------------------------------------------
+double
+Engine::mem_capacity_bytes() const
+{
+  if (opts_.mem_mode == PGN_MEM_NATIVE) {
+    size_t f = 0, t = 0;
+    cudaMemGetInfo(&f, &t);
+    const double frac = opts_.native_mem_fraction > 0 ? opts_.native_mem_fraction : 0.85;
+    // what is free now plus what this engine already holds
+    const DeviceBuf* mine[] = {&left_[0], &left_[1], &length_[0], &length_[1], &est_, &err_raw_,
+                               &err_ref_, &axis_, &active_, &par_est_[0], &par_est_[1],
+                               &par_err_[0], &par_err_[1]};
+    size_t held = 0;
+    for (const DeviceBuf* b : mine)
+      held += b->bytes;
+    return frac * static_cast<double>(f + held) * (comm_ ? comm_->nranks : 1);
+  }
+  return 16e9;  // heuristic_classifier.cuh:89-94
+}
+
+int
+Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, double fin_err,
+                           double cum_err, HeuristicOutcome* out)
+{
+  (void)iter_est;
+  // heuristic_classifier.cuh:105-145, 227-264: bytes a full split of n regions would need
+  const size_t nd = static_cast<size_t>(ndim_);
+  const size_t doubles = n_global * (10 * nd + 8);
+  const size_t ints = 4 * n_global;
+  const size_t required = 8 * doubles + 4 * ints;
+  const size_t total = static_cast<size_t>(mem_capacity_bytes());
+  const size_t free_mem = total > required ? total - required : 1;
+  const double ratio = static_cast<double>(required) / static_cast<double>(free_mem);
+  const bool necessary = ratio > 1.;
+  const bool criteria = ratio > 1. || (ratio > .1 && tracker_.converged());
+  if (!criteria) {
+    out->must_terminate = necessary;
+    return PGN_OK;
+  }
+  out->ran = true;
+
+  // Heuristic_classifier::classify (heuristic_classifier.cuh:362-451)
+  if (comm_ && comm_->nranks > 1) {
+    // min/max of the errors over all ranks (the local ones are still in stats_dev_)
+    PGN_CUDA(cudaMemcpyAsync(stats_glob_.as<double>() + kNegMinSlot,
+                             stats_dev_.as<double>() + kNegMinSlot, sizeof(double) * 2,
+                             cudaMemcpyDeviceToDevice, stream_));
+    PGN_TRY(comm_->allreduce(stats_glob_.as<double>() + kNegMinSlot, 2, kOpMax, stream_));
+    PGN_CUDA(cudaMemcpyAsync(host_global_ + kNegMinSlot, stats_glob_.as<double>() + kNegMinSlot,
+                             sizeof(double) * 2, cudaMemcpyDeviceToHost, stream_));
+    PGN_CUDA(cudaStreamSynchronize(stream_));
+  }
+  const double min_err = -host_global_[kNegMinSlot];
+  const double max_err = host_global_[kMaxSlot];
+
+  double range_lo = min_err, range_hi = max_err;
+  double threshold = iter_err / static_cast<double>(n_global);
+  const double target_error = std::fabs(tracker_.last[2]) * tracker_.epsrel;
+  bool pass_mem = false, pass_budget = false;
+  size_t num_active = 0;
+  double finished_errorest = 0.;
+  double active_err_sum = 0.;
+  size_t increases = 0, decreases = 0;
+
+  auto probe = [&]() -> int {
+    PGN_TRY(run_threshold(0, threshold));
+    PGN_TRY(sync_stats(false));
+    out->probes++;
+    num_active = static_cast<size_t>(host_global_[kNumActive]);
+    active_err_sum = host_global_[kSumActErr];
+    const double pct =
+      static_cast<double>(static_cast<int>(num_active)) / static_cast<double>(static_cast<int>(n_global));
+    pass_mem = pct <= max_active_regions_percentage_;
+    return PGN_OK;
+  };
+
+  do {
+    if (!pass_mem && increases <= 20) {
+      pass_mem = false;
+      size_t attempts = 0;
+      while (!pass_mem && attempts < 20) {
+        PGN_TRY(probe());
+        if (!pass_mem) {
+          range_lo = threshold;
+          threshold += std::fabs(range_hi - threshold) * .5;
+        }
+        attempts++;
+      }
+      increases++;
+    }
+    if (pass_mem) {
+      const double extra = iter_err - active_err_sum - fin_err;
+      const double budget = target_error - cum_err;
+      pass_budget = extra <= max_percent_error_budget_ * budget;
+      finished_errorest = extra;
+      if (!pass_budget && decreases <= 20) {
+        range_hi = threshold;
+        threshold -= std::fabs(range_lo - threshold) * .5;
+        pass_mem = false;
+        decreases++;
+      }
+    }
+    const bool exhausted = decreases >= 20 || increases >= 20;
+    if (exhausted && max_percent_error_budget_ < .7) {
+      max_percent_error_budget_ += 0.1;
+      decreases = 0;
+      increases = 0;
+      range_lo = min_err;
+      range_hi = max_err;
+      threshold = iter_err / static_cast<double>(n_global);
+    } else if (exhausted && max_percent_error_budget_ >= .7 &&
+               max_active_regions_percentage_ <= .7) {
+      max_active_regions_percentage_ += .1;
+    } else if (exhausted) {
+      break;
+    }
+  } while (!pass_mem || !pass_budget);
+
+  max_active_regions_percentage_ = .5;
+  max_percent_error_budget_ = .25;
+
+  out->success = pass_mem && pass_budget;
+  out->num_active = num_active;
+  out->finished_errorest = finished_errorest;
+  out->threshold = threshold;
+  if (out->success) {
+    // adopt the threshold flags (Workspace.cuh:104-112)
+    PGN_TRY(run_threshold(1, threshold));
+    PGN_TRY(sync_stats(false));
+    out->num_active = static_cast<size_t>(host_global_[kNumActive]);
+  }
+  out->must_terminate = (!out->success && necessary) || out->num_active == 0;
+  return PGN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the loop (Workspace::integrate)
+// ------------------------------------------------------------------------------------------------
+int
+Engine::integrate(pgn_eval_fn fn, void* user, const pgn_integrate_args& args, pgn_result_t* out)
+{
+  if (!fn || !out)
+    return PGN_ERR_INVALID;
+  PGN_CUDA(cudaSetDevice(device_));
+  const double epsrel = args.epsrel, epsabs = args.epsabs;
+  const int relerr = args.relerr_classification;
+  const int max_iters = opts_.max_iters > 0 ? opts_.max_iters : 700;
+  const bool multi = comm_ && comm_->nranks > 1;
+  const bool tracing = opts_.trace != 0;
+
+  std::memset(out, 0, sizeof *out);
+  out->status = 1;
+  out->lastPhase = -1;
+  trace_.clear();
+  tracker_.reset(epsrel, epsabs);
+  max_percent_error_budget_ = .25;
+  max_active_regions_percentage_ = .5;
+
+  if (!args.use_current_regions) {
+    const int parts = ndim_ < 5 ? 4 : (ndim_ <= 10 ? 2 : 1);  // Workspace.cuh:379-385
+    PGN_TRY(regions_init_uniform(parts));
+  }
+  if (filtered_pending_) {
+    set_last_error("integrate() between filter() and split()");
+    return PGN_ERR_STATE;
+  }
+  parents_n_ = 0;  // the reference starts every call without parent estimates (:165, :375)
+
+  size_t n_global = n_;
+  if (multi) {
+    double h = static_cast<double>(n_);
+    PGN_CUDA(cudaMemcpyAsync(stats_glob_.ptr, &h, sizeof h, cudaMemcpyHostToDevice, stream_));
+    PGN_TRY(comm_->allreduce(stats_glob_.as<double>(), 1, kOpSum, stream_));
+    PGN_CUDA(cudaMemcpyAsync(&h, stats_glob_.ptr, sizeof h, cudaMemcpyDeviceToHost, stream_));
+    PGN_CUDA(cudaStreamSynchronize(stream_));
+    n_global = static_cast<size_t>(h);
+  }
+
+  double cum_est = 0., cum_err = 0.;
+  uint64_t nregions = 0, iters = 0, neval = 0;
+  int status = 1;
+  bool done = false;
+
+  for (int it = 0; it < max_iters && n_global > 0 && !done; ++it) {
+    pgn_iter_stats st;
+    std::memset(&st, 0, sizeof st);
+    st.iteration = it;
+    st.nregions = n_;
+    st.nregions_global = n_global;
+
+    if (tracing)
+      cudaEventRecord(ev_[0], stream_);
+    PGN_TRY(launch_evaluate(fn, user));
+    evaluated_ = true;
+    if (tracing)
+      cudaEventRecord(ev_[1], stream_);
+    PGN_TRY(run_classify(epsrel, relerr));
+    if (tracing)
+      cudaEventRecord(ev_[2], stream_);
+    PGN_TRY(sync_stats(false));
+    neval += static_cast<uint64_t>(n_global) * rule_.feval;
+
+    const double iter_est = host_global_[kSumEst];
+    const double iter_err = host_global_[kSumErr];
+    if (opts_.trace_arrays) {
+      digest_arrays(&st, false);
+      digest_arrays(&st, true);
+    }
+    if (tracing) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev_[0], ev_[1]);
+      st.eval_ms = ms;
+      cudaEventElapsedTime(&ms, ev_[1], ev_[2]);
+      st.classify_ms = ms;
+    }
+    st.iter_estimate = iter_est;
+    st.iter_errorest = iter_err;
+
+    if (args.iters_mode == PGN_ITERS_BEFORE_CHECK)
+      iters++;
+
+    // accuracy_reached (PaganiUtils.cuh:387-394)
+    {
+      const double e = std::fabs(cum_est + iter_est), r = cum_err + iter_err;
+      if (r / e <= epsrel || r <= epsabs) {
+        cum_est += iter_est;
+        cum_err += iter_err;
+        status = 0;
+        nregions += n_global;
+        st.cum_estimate = cum_est;
+        st.cum_errorest = cum_err;
+        if (tracing)
+          trace_.push_back(st);
+        done = true;
+        break;
+      }
+    }
+
+    tracker_.store(cum_est + iter_est);
+    double fin_est = iter_est - host_global_[kSumActEst];  // compute_finished_estimates
+    double fin_err = iter_err - host_global_[kSumActErr];
+    size_t m_global = static_cast<size_t>(host_global_[kNumActive]);
+    // the probes of the heuristic search overwrite the statistics: remember the accepted flags'
+    size_t m_local = static_cast<size_t>(host_local_[kNumActive]);
+    std::vector<size_t> counts = rank_counts_;
+
+    // fix_error_budget_overflow (Workspace.cuh:121-146)
+    if (cum_err + fin_err > std::fabs(cum_est + iter_est) * epsrel) {
+      PGN_TRY(run_threshold(2, 0.0));
+      PGN_TRY(sync_stats(false));
+      fin_est = 0.;
+      fin_err = 0.;
+      m_global = static_cast<size_t>(host_global_[kNumActive]);
+      m_local = static_cast<size_t>(host_local_[kNumActive]);
+      counts = rank_counts_;
+      st.budget_overflow = 1;
+    }
+
+    HeuristicOutcome hs;
+    if (tracing)
+      cudaEventRecord(ev_[2], stream_);
+    PGN_TRY(heuristic_classify(n_global, iter_est, iter_err, fin_err, cum_err, &hs));
+    st.heuristic_ran = hs.ran;
+    st.heuristic_probes = hs.probes;
+    st.threshold = hs.threshold;
+    if (hs.success) {
+      fin_est = iter_est - host_global_[kSumActEst];
+      fin_err = hs.finished_errorest;
+      m_global = hs.num_active;
+      m_local = static_cast<size_t>(host_local_[kNumActive]);
+      counts = rank_counts_;
+      if (opts_.trace_arrays)
+        st.dig_active = digest_device(active_.ptr, 1, n_);
+    }
+    if (hs.must_terminate) {
+      cum_est += iter_est;
+      cum_err += iter_err;
+      nregions += n_global;
+      st.cum_estimate = cum_est;
+      st.cum_errorest = cum_err;
+      st.nactive = m_global;
+      if (tracing)
+        trace_.push_back(st);
+      done = true;
+      break;
+    }
+    cum_est += fin_est;
+    cum_err += fin_err;
+    st.finished_estimate = fin_est;
+    st.finished_errorest = fin_err;
+    st.cum_estimate = cum_est;
+    st.cum_errorest = cum_err;
+    st.nactive = m_global;
+
+    // filter + split
+    nregions += n_global - m_global;
+    if (tracing)
+      cudaEventRecord(ev_[3], stream_);
+    if (m_global == 0) {
+      n_ = 0;
+      n_global = 0;
+      parents_n_ = 0;
+    } else {
+      rank_counts_ = counts;
+      bool rebalanced = false;
+      PGN_TRY(compact_and_split(m_local, m_global, &rebalanced));
+      st.rebalanced = rebalanced;
+      n_global = 2 * m_global;
+    }
+    if (tracing) {
+      cudaEventRecord(ev_[4], stream_);
+      cudaEventSynchronize(ev_[4]);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev_[2], ev_[3]);
+      st.heuristic_ms = ms;
+      cudaEventElapsedTime(&ms, ev_[3], ev_[4]);
+      st.split_ms = ms;
+      trace_.push_back(st);
+    }
+    evaluated_ = classified_ = false;
+    if (args.iters_mode == PGN_ITERS_AFTER_SPLIT)
+      iters++;
+  }
+  if (!done)
+    nregions += n_global;
+  PGN_CUDA(cudaStreamSynchronize(stream_));
+
+  out->estimate = cum_est;
+  out->errorest = cum_err;
+  out->neval = neval;
+  out->nregions = nregions;
+  out->nFinishedRegions = 0;
+  out->status = status;
+  out->lastPhase = -1;
+  out->chi_sq = 0.;
+  out->iters = iters;
+  return PGN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int
+Engine::comm_init_nccl(const uint8_t* id, int nranks, int rank)
+{
+  if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks)
+    return PGN_ERR_INVALID;
+  PGN_CUDA(cudaSetDevice(device_));
+  delete comm_;
+  comm_ = nullptr;
+  std::string err;
+  comm_ = make_nccl_comm(id, nranks, rank, &err);
+  if (!comm_) {
+    set_last_error("NCCL: " + err);
+    return PGN_ERR_NCCL;
+  }
+  rank_counts_.assign(nranks, 0);
+  return PGN_OK;
+}
+
+int
+Engine::comm_init_host(int nranks, int rank, pgn_allreduce_fn ar, pgn_alltoallv_fn a2a, void* user)
+{
+  if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks || !ar || !a2a)
+    return PGN_ERR_INVALID;
+  delete comm_;
+  comm_ = make_host_comm(nranks, rank, ar, a2a, user);
+  rank_counts_.assign(nranks, 0);
+  return PGN_OK;
+}
+
+int
+Engine::comm_size(int* nranks, int* rank) const
+{
+  if (nranks)
+    *nranks = comm_ ? comm_->nranks : 1;
+  if (rank)
+    *rank = comm_ ? comm_->rank : 0;
+  return PGN_OK;
+}
+
+}  // namespace pgn

@@ -1,0 +1,489 @@
+// HBM-bound stages of one PAGANI iteration, written for sm_100a: every stage is ONE pass over the
+// SoA arrays with fully coalesced accesses, fixed-shape (hence run-to-run deterministic) reductions
+// and no host round trips inside a stage.
+//
+//   k_uniform_split   create_uniform_split             (reference Sub_regions.cuh:11-36)
+//   k_classify        RefineError + set_array_to_value + 2x thrust::reduce + 2x thrust::inner_product
+//                     + the flag count                  (Phases.cuh:219-268, PaganiUtils.cuh:310-311,
+//                                                        368-385, thrust_utils.cuh:16-47)
+//   k_threshold       device_set_true_for_larger_than + reduce + inner_product of one probe of
+//                     Heuristic_classifier::classify    (heuristic_classifier.cuh:60-72, 283-325)
+//   k_compact         thrust::exclusive_scan + alignRegions [+ divideIntervalsGPU when fused]
+//                                                        (Sub_region_filter.cuh:8-47, 61-139,
+//                                                         Sub_region_splitter.cuh:8-46)
+//   k_split           divideIntervalsGPU alone          (Sub_region_splitter.cuh:8-46)
+//
+// Regions are processed in tiles of kTile = 1024 (one 256-thread block, 4 rounds).  A stage that
+// (re)writes the active flags also leaves the number of active regions of each tile and their
+// exclusive prefix, so compaction never needs a separate scan over the flags.
+#ifndef PGN_STAGES_CUH
+#define PGN_STAGES_CUH
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace pgn {
+
+constexpr int kBlock = 256;
+constexpr int kRounds = 4;
+constexpr int kTile = kBlock * kRounds;
+
+// slots of the per-stage statistics vector (device + pinned host mirror)
+enum Stat {
+  kSumEst = 0,
+  kSumErr = 1,
+  kSumActEst = 2,
+  kSumActErr = 3,
+  kNumActive = 4,
+  kMinErr = 5,
+  kMaxErr = 6,
+  kStatCount = 8
+};
+
+struct TileScratch {
+  double* partials;       // [tiles][kStatCount]
+  uint32_t* tile_count;   // [tiles]   active regions per tile
+  uint64_t* tile_offset;  // [tiles]   exclusive prefix of tile_count
+  unsigned int* done;     // arrival counter (self-resetting)
+  double* stats;          // [kStatsLen] final values, see below
+  int rank, nranks;       // for the one-hot per-rank active count
+};
+// layout of `stats`: [0,8) the Stat slots; [8] = -min(err), [9] = max(err) (so one MAX all-reduce
+// serves both); [16 + r] = active regions of rank r (zero except the own rank: a SUM all-reduce of
+// the whole vector leaves every rank with every rank's count).
+constexpr int kNegMinSlot = 8;
+constexpr int kMaxSlot = 9;
+constexpr int kRankSlot = 16;
+constexpr int kMaxRanks = 16;
+constexpr int kStatsLen = kRankSlot + kMaxRanks;
+
+__global__ void
+k_uniform_split(double* left, double* length, size_t n, int parts, int ndim, double edge)
+{
+  const size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n)
+    return;
+  size_t q = t;
+  for (int d = 0; d < ndim; ++d) {
+    const size_t id = q % parts;
+    q /= parts;
+    left[static_cast<size_t>(d) * n + t] = static_cast<double>(id) * edge;
+    length[static_cast<size_t>(d) * n + t] = edge;
+  }
+}
+
+namespace dev {
+
+struct Acc {
+  double v[5];  // the five sums
+  double mn, mx;
+};
+
+__device__ __forceinline__ void
+acc_zero(Acc& a)
+{
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+    a.v[i] = 0.0;
+  a.mn = __longlong_as_double(0x7ff0000000000000LL);   // +inf
+  a.mx = __longlong_as_double(0xfff0000000000000LL);   // -inf
+}
+
+__device__ __forceinline__ void
+acc_merge(Acc& a, const Acc& b)
+{
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+    a.v[i] += b.v[i];
+  a.mn = fmin(a.mn, b.mn);
+  a.mx = fmax(a.mx, b.mx);
+}
+
+__device__ __forceinline__ Acc
+acc_shfl_xor(const Acc& a, int off)
+{
+  Acc b;
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+    b.v[i] = __shfl_xor_sync(0xffffffffu, a.v[i], off);
+  b.mn = __shfl_xor_sync(0xffffffffu, a.mn, off);
+  b.mx = __shfl_xor_sync(0xffffffffu, a.mx, off);
+  return b;
+}
+
+// fixed-shape block reduction; result valid in thread 0
+__device__ __forceinline__ Acc
+block_reduce(Acc a, Acc* s_warp /*[kBlock/32]*/)
+{
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+    acc_merge(a, acc_shfl_xor(a, off));
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0)
+    s_warp[w] = a;
+  __syncthreads();
+  if (w == 0) {
+    if (lane < kBlock / 32)
+      a = s_warp[lane];
+    else
+      acc_zero(a);
+#pragma unroll
+    for (int off = (kBlock / 32) / 2; off > 0; off >>= 1)
+      acc_merge(a, acc_shfl_xor(a, off));
+  }
+  __syncthreads();
+  return a;
+}
+
+// Executed by every block after it stored its partial: the last block to arrive folds the
+// partials in a fixed order, writes the final statistics and the exclusive prefix of the tile
+// counts, and re-arms the counter.
+__device__ __forceinline__ void
+finalize(const TileScratch& ts, unsigned int tiles, bool with_offsets, Acc* s_warp, uint64_t* s_scan)
+{
+  __shared__ bool s_last;
+  __threadfence();
+  if (threadIdx.x == 0)
+    s_last = atomicAdd(ts.done, 1u) == tiles - 1;
+  __syncthreads();
+  if (!s_last)
+    return;
+  __threadfence();
+  Acc a;
+  acc_zero(a);
+  for (unsigned int b = threadIdx.x; b < tiles; b += kBlock) {
+    const double* p = ts.partials + static_cast<size_t>(b) * kStatCount;
+    Acc t;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+      t.v[i] = __ldcg(&p[i]);
+    t.mn = __ldcg(&p[kMinErr]);
+    t.mx = __ldcg(&p[kMaxErr]);
+    acc_merge(a, t);
+  }
+  a = block_reduce(a, s_warp);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+      ts.stats[i] = a.v[i];
+    ts.stats[kMinErr] = a.mn;
+    ts.stats[kMaxErr] = a.mx;
+    ts.stats[kNegMinSlot] = -a.mn;
+    ts.stats[kMaxSlot] = a.mx;
+    for (int r = 0; r < ts.nranks; ++r)
+      ts.stats[kRankSlot + r] = r == ts.rank ? a.v[kNumActive] : 0.0;
+    *ts.done = 0u;
+  }
+  if (with_offsets) {
+    const unsigned int chunk = (tiles + kBlock - 1) / kBlock;
+    const unsigned int lo = threadIdx.x * chunk;
+    const unsigned int hi = lo + chunk < tiles ? lo + chunk : tiles;
+    uint64_t local = 0;
+    for (unsigned int b = lo; b < hi; ++b)
+      local += __ldcg(&ts.tile_count[b]);
+    s_scan[threadIdx.x] = local;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the 256 chunk sums
+    for (int off = 1; off < kBlock; off <<= 1) {
+      const uint64_t add = threadIdx.x >= off ? s_scan[threadIdx.x - off] : 0;
+      __syncthreads();
+      s_scan[threadIdx.x] += add;
+      __syncthreads();
+    }
+    uint64_t run = s_scan[threadIdx.x] - local;
+    for (unsigned int b = lo; b < hi; ++b) {
+      ts.tile_offset[b] = run;
+      run += __ldcg(&ts.tile_count[b]);
+    }
+  }
+}
+
+}  // namespace dev
+
+// One pass: (optional) two-level error refinement, relative-error flag, all iteration sums.
+// REFINE=false is iteration 0 of the reference loop (no parents yet: hybrid.cuh:26-28 returns
+// early, every region stays active and the raw errors are the errors).
+template <bool REFINE>
+__global__ void __launch_bounds__(kBlock)
+k_classify(const double* __restrict__ est, const double* __restrict__ err_raw,
+           const double* __restrict__ parent_est, double* __restrict__ err_out,
+           uint8_t* __restrict__ active, size_t n, double epsrel, int relerr_classification,
+           TileScratch ts)
+{
+  __shared__ dev::Acc s_warp[kBlock / 32];
+  __shared__ uint64_t s_scan[kBlock];
+  const size_t half = n >> 1;
+  const size_t base = static_cast<size_t>(blockIdx.x) * kTile;
+  dev::Acc a;
+  dev::acc_zero(a);
+#pragma unroll
+  for (int q = 0; q < kRounds; ++q) {
+    const size_t i = base + static_cast<size_t>(q) * kBlock + threadIdx.x;
+    if (i < n) {
+      const double self_est = est[i];
+      double e = err_raw[i];
+      double flag = 1.0;
+      if constexpr (REFINE) {
+        const bool right = (i + i) >= n;
+        const size_t sib = right ? i - half : i + half;
+        const size_t par = right ? i - half : i;
+        const double sib_est = est[sib];
+        const double sib_err = err_raw[sib];
+        const double par_est = parent_est[par];
+        // Phases.cuh:251-261 with the rounding sequence of the reference's machine code
+        const double diff = fabs(__dmul_rn(__dsub_rn(__dadd_rn(self_est, sib_est), par_est), 0.25));
+        const double both = __dadd_rn(e, sib_err);
+        if (both > 0.0) {
+          const double c = __dadd_rn(__ddiv_rn(__dadd_rn(diff, diff), both), 1.0);
+          e = __dmul_rn(e, c);
+        }
+        e = __dadd_rn(diff, e);
+        err_out[i] = e;
+        if (relerr_classification) {
+          const double tol = fmax(__dmul_rn(epsrel, fabs(self_est)), 1e-200);
+          flag = (e < tol) ? 0.0 : 1.0;
+        }
+      }
+      active[i] = flag != 0.0 ? 1 : 0;
+      a.v[kSumEst] += self_est;
+      a.v[kSumErr] += e;
+      a.v[kSumActEst] += flag * self_est;  // thrust::inner_product(flags, estimates)
+      a.v[kSumActErr] += flag * e;
+      a.v[kNumActive] += flag;
+      a.mn = fmin(a.mn, e);
+      a.mx = fmax(a.mx, e);
+    }
+  }
+  a = dev::block_reduce(a, s_warp);
+  if (threadIdx.x == 0) {
+    double* p = ts.partials + static_cast<size_t>(blockIdx.x) * kStatCount;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+      p[i] = a.v[i];
+    p[kMinErr] = a.mn;
+    p[kMaxErr] = a.mx;
+    ts.tile_count[blockIdx.x] = static_cast<uint32_t>(a.v[kNumActive]);
+  }
+  dev::finalize(ts, gridDim.x, true, s_warp, s_scan);
+}
+
+// One probe of the heuristic threshold search: flag = err > threshold.
+// MODE 0: count + sum(flag*err) only (nothing written);  MODE 1: also write the flags, the tile
+// counts/prefix and sum(flag*est) (the accepted threshold);  MODE 2: re-activate everything
+// (Workspace::fix_error_budget_overflow, Workspace.cuh:135-145).
+template <int MODE>
+__global__ void __launch_bounds__(kBlock)
+k_threshold(const double* __restrict__ est, const double* __restrict__ err, uint8_t* __restrict__ active,
+            size_t n, double threshold, TileScratch ts)
+{
+  __shared__ dev::Acc s_warp[kBlock / 32];
+  __shared__ uint64_t s_scan[kBlock];
+  const size_t base = static_cast<size_t>(blockIdx.x) * kTile;
+  dev::Acc a;
+  dev::acc_zero(a);
+#pragma unroll
+  for (int q = 0; q < kRounds; ++q) {
+    const size_t i = base + static_cast<size_t>(q) * kBlock + threadIdx.x;
+    if (i < n) {
+      const double e = err[i];
+      const double flag = (MODE == 2) ? 1.0 : ((e > threshold) ? 1.0 : 0.0);
+      a.v[kSumActErr] += flag * e;
+      a.v[kNumActive] += flag;
+      if (MODE != 0) {
+        const double v = est[i];
+        a.v[kSumActEst] += flag * v;
+        active[i] = flag != 0.0 ? 1 : 0;
+      }
+    }
+  }
+  a = dev::block_reduce(a, s_warp);
+  if (threadIdx.x == 0) {
+    double* p = ts.partials + static_cast<size_t>(blockIdx.x) * kStatCount;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+      p[i] = a.v[i];
+    p[kMinErr] = a.mn;
+    p[kMaxErr] = a.mx;
+    if (MODE != 0)
+      ts.tile_count[blockIdx.x] = static_cast<uint32_t>(a.v[kNumActive]);
+  }
+  dev::finalize(ts, gridDim.x, MODE != 0, s_warp, s_scan);
+}
+
+// Recount after the flags were overwritten from outside (pgn_set_active).
+__global__ void __launch_bounds__(kBlock)
+k_recount(const double* __restrict__ est, const double* __restrict__ err,
+          const uint8_t* __restrict__ active, size_t n, TileScratch ts)
+{
+  __shared__ dev::Acc s_warp[kBlock / 32];
+  __shared__ uint64_t s_scan[kBlock];
+  const size_t base = static_cast<size_t>(blockIdx.x) * kTile;
+  dev::Acc a;
+  dev::acc_zero(a);
+#pragma unroll
+  for (int q = 0; q < kRounds; ++q) {
+    const size_t i = base + static_cast<size_t>(q) * kBlock + threadIdx.x;
+    if (i < n) {
+      const double flag = active[i] ? 1.0 : 0.0;
+      const double e = err[i], v = est[i];
+      a.v[kSumEst] += v;
+      a.v[kSumErr] += e;
+      a.v[kSumActEst] += flag * v;
+      a.v[kSumActErr] += flag * e;
+      a.v[kNumActive] += flag;
+      a.mn = fmin(a.mn, e);
+      a.mx = fmax(a.mx, e);
+    }
+  }
+  a = dev::block_reduce(a, s_warp);
+  if (threadIdx.x == 0) {
+    double* p = ts.partials + static_cast<size_t>(blockIdx.x) * kStatCount;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+      p[i] = a.v[i];
+    p[kMinErr] = a.mn;
+    p[kMaxErr] = a.mx;
+    ts.tile_count[blockIdx.x] = static_cast<uint32_t>(a.v[kNumActive]);
+  }
+  dev::finalize(ts, gridDim.x, true, s_warp, s_scan);
+}
+
+struct CompactArgs {
+  const double* left;       // [ndim][n]
+  const double* length;     // [ndim][n]
+  const double* est;        // [n]
+  const double* err;        // [n]   (refined)
+  const int32_t* axis;      // [n]
+  const uint8_t* active;    // [n]
+  const uint64_t* tile_offset;
+  size_t n;
+  size_t m;                 // number of active regions (known on the host before the launch)
+  double* out_left;         // FUSED: [ndim][2m]   else [ndim][m]
+  double* out_length;
+  double* parent_est;       // [m]
+  double* parent_err;       // [m]
+  int32_t* out_axis;        // [m] (only when not fused)
+  int ndim;
+};
+
+// Stable stream compaction of the active regions; FUSED additionally bisects each survivor along
+// its split axis and writes both children at the reference's indices j (left half) and m + j
+// (right half) of the next region list, so every surviving parent is read once and its children
+// written once.
+template <bool FUSED>
+__global__ void __launch_bounds__(kBlock)
+k_compact(const CompactArgs A)
+{
+  __shared__ uint32_t s_wsum[kBlock / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const size_t base = static_cast<size_t>(blockIdx.x) * kTile;
+  uint64_t run = A.tile_offset[blockIdx.x];
+  const size_t out_stride = FUSED ? 2 * A.m : A.m;
+#pragma unroll 1
+  for (int q = 0; q < kRounds; ++q) {
+    const size_t i = base + static_cast<size_t>(q) * kBlock + threadIdx.x;
+    const bool on = i < A.n && A.active[i] != 0;
+    const unsigned int ballot = __ballot_sync(0xffffffffu, on);
+    if (lane == 0)
+      s_wsum[w] = __popc(ballot);
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < kBlock / 32; ++k) {
+      const uint32_t c = s_wsum[k];
+      before += k < w ? c : 0;
+      total += c;
+    }
+    __syncthreads();
+    if (on) {
+      const size_t j = run + before + __popc(ballot & ((1u << lane) - 1u));
+      const int ax = A.axis[i];
+      A.parent_est[j] = A.est[i];
+      A.parent_err[j] = A.err[i];
+      if (!FUSED)
+        A.out_axis[j] = ax;
+      for (int d = 0; d < A.ndim; ++d) {
+        const double lo = A.left[static_cast<size_t>(d) * A.n + i];
+        const double ln = A.length[static_cast<size_t>(d) * A.n + i];
+        double* ol = A.out_left + static_cast<size_t>(d) * out_stride;
+        double* ow = A.out_length + static_cast<size_t>(d) * out_stride;
+        if (FUSED) {
+          if (d == ax) {
+            const double h = __ddiv_rn(ln, 2.0);   // Sub_region_splitter.cuh:33-35
+            ol[j] = lo;
+            ol[A.m + j] = __dadd_rn(lo, h);        // left + 1 * interval_length
+            ow[j] = h;
+            ow[A.m + j] = h;
+          } else {
+            ol[j] = lo;
+            ol[A.m + j] = lo;
+            ow[j] = ln;
+            ow[A.m + j] = ln;
+          }
+        } else {
+          ol[j] = lo;
+          ow[j] = ln;
+        }
+      }
+    }
+    run += total;
+  }
+}
+
+// Bisection alone (stage-level API and the rebalancing iterations of the multi-GPU path).
+__global__ void __launch_bounds__(kBlock)
+k_split(const double* __restrict__ left, const double* __restrict__ length,
+        const int32_t* __restrict__ axis, size_t m, int ndim, double* __restrict__ out_left,
+        double* __restrict__ out_length)
+{
+  const size_t j = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j >= m)
+    return;
+  const int ax = axis[j];
+  for (int d = 0; d < ndim; ++d) {
+    const double lo = left[static_cast<size_t>(d) * m + j];
+    const double ln = length[static_cast<size_t>(d) * m + j];
+    double* ol = out_left + static_cast<size_t>(d) * 2 * m;
+    double* ow = out_length + static_cast<size_t>(d) * 2 * m;
+    if (d == ax) {
+      const double h = __ddiv_rn(ln, 2.0);
+      ol[j] = lo;
+      ol[m + j] = __dadd_rn(lo, h);
+      ow[j] = h;
+      ow[m + j] = h;
+    } else {
+      ol[j] = lo;
+      ol[m + j] = lo;
+      ow[j] = ln;
+      ow[m + j] = ln;
+    }
+  }
+}
+
+// digest64(x) = sum_i bits(x[i]) * (2i+1)  (mod 2^64); modular sums commute, so atomics are exact.
+template <typename T>
+__global__ void
+k_digest(const T* __restrict__ x, size_t n, unsigned long long* out)
+{
+  unsigned long long acc = 0;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    unsigned long long bits;
+    if (sizeof(T) == 8)
+      bits = *reinterpret_cast<const unsigned long long*>(&x[i]);
+    else if (sizeof(T) == 4)
+      bits = *reinterpret_cast<const unsigned int*>(&x[i]);
+    else
+      bits = *reinterpret_cast<const unsigned char*>(&x[i]);
+    acc += bits * (2ull * i + 1ull);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+    acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0)
+    atomicAdd(out, acc);
+}
+
+}  // namespace pgn
+#endif

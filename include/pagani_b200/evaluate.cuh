@@ -1,0 +1,438 @@
+// Region-evaluation kernel of the B200-native PAGANI engine (header template: it is compiled with
+// the caller's integrand functor inlined, everything else lives behind the C ABI in pagani_b200.h).
+//
+// Replaces quad::INTEGRATE_GPU_PHASE1 -> INIT_REGION_POOL -> SampleRegionBlock -> computePermutation
+// (reference cuda/pagani/quad/GPUquad/Phases.cuh:301-404, Sample.cuh:49-290) and is BIT-IDENTICAL
+// to it per region (estimate, error, split axis), by construction:
+//
+//  * The reference runs one 64-thread block per region; thread t accumulates points t, t+64, ...
+//    into 5 rule sums with fma(fun, w, sum), reduces each warp with a shuffle-down tree and adds
+//    the two warp results.  Here ONE WARP owns a region and every lane plays reference threads
+//    `lane` (accumulator set A) and `lane+32` (set B): the same per-thread chains, the same tree
+//    (A and B are reduced in the two half-warps after one xor-16 exchange), the same final A+B.
+//    No __syncthreads, no thread-0 serial sections, two independent integrand evaluations in
+//    flight per lane to keep the FP64 pipe fed.
+//  * The affine map region->integration volume is evaluated with the reference's exact operation
+//    sequence (x = fma(range, fma(.5+g, lo, (.5-g)*hi), low); checked against its PTX) but only
+//    once per (axis, generator value): a coordinate can take just 11 values per axis, so each warp
+//    builds an 11 x ndim table in shared memory per region and a point becomes ndim table look-ups
+//    driven by one packed 4-bit-per-axis code word (staged in shared memory with the weights).
+//  * Fourth differences (split axis) and the 27 null-rule terms are computed lane-parallel; max and
+//    first-wins argmax are order independent, so this does not change results.
+//
+// Persistent launch: grid = SMs x resident blocks, warps stride over the region list.
+#ifndef PAGANI_B200_EVALUATE_CUH
+#define PAGANI_B200_EVALUATE_CUH
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <new>
+#include <type_traits>
+#include <utility>
+
+#include "../pagani_b200.h"
+
+namespace pagani_b200 {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kWeightRow = 6;  // 5 rule weights padded to 48 B so a row is three 16-byte loads
+
+namespace detail {
+
+template <class F, size_t N, size_t... I>
+__device__ __forceinline__ double
+apply_impl(F& f, const double (&x)[N], std::index_sequence<I...>)
+{
+  return f(x[I]...);
+}
+
+// call f(x[0], ..., x[N-1])   (reference: gpu::apply, common/cuda/cudaApply.cuh:18-26)
+template <class F, size_t N>
+__device__ __forceinline__ double
+apply(F& f, const double (&x)[N])
+{
+  return apply_impl(f, x, std::make_index_sequence<N>());
+}
+
+struct EvalParams {
+  const double* left;
+  const double* length;
+  size_t n;
+  double* estimate;
+  double* errorest;
+  int32_t* axis;
+  const uint64_t* point_code;
+  const double* weights;
+  const double* scale;
+  const double* norm;
+  double lows[PGN_MAX_NDIM + 1];
+  double ranges[PGN_MAX_NDIM + 1];
+  double half_plus_g[PGN_NCODES];
+  double half_minus_g[PGN_NCODES];
+  double jacobian;
+  double ratio;
+  int feval;
+};
+
+template <int NDIM>
+__host__ __device__ constexpr int
+per_warp_doubles()
+{
+  // coordinate table, first-chunk function values, lower, upper, extent
+  return NDIM * PGN_NCODES + 64 + 3 * NDIM;
+}
+
+template <int NDIM>
+__host__ __device__ constexpr size_t
+smem_bytes(int feval, bool codes_in_smem)
+{
+  return sizeof(double) * (PGN_NSETS * kWeightRow + 2 * PGN_NSETS * PGN_NRULES + 2 * PGN_NCODES +
+                           kWarpsPerBlock * per_warp_doubles<NDIM>()) +
+         (codes_in_smem ? sizeof(uint64_t) * static_cast<size_t>(feval) : 0);
+}
+
+// first-wins arg-max over lanes (value v >= 0, index idx); ties go to the smaller index
+template <int WIDTH>
+__device__ __forceinline__ void
+warp_argmax_first(double& v, int& idx)
+{
+#pragma unroll
+  for (int off = WIDTH / 2; off > 0; off >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+    if (ov > v || (ov == v && oi < idx)) {
+      v = ov;
+      idx = oi;
+    }
+  }
+}
+
+template <typename F, int NDIM, bool BY_VALUE, bool CODES_IN_SMEM>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+evaluate_kernel(typename std::conditional<BY_VALUE, F, F*>::type fparam, const EvalParams P)
+{
+  static_assert(NDIM >= 2 && NDIM <= PGN_MAX_NDIM, "4*ndim+1 must fit the 64 emulated threads");
+  constexpr int kArgWidth = NDIM <= 16 ? 16 : 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+
+  double* s_w = reinterpret_cast<double*>(smem_raw);         // [9][6]
+  double* s_scale = s_w + PGN_NSETS * kWeightRow;            // [9][5]
+  double* s_norm = s_scale + PGN_NSETS * PGN_NRULES;         // [9][5]
+  double* s_tp = s_norm + PGN_NSETS * PGN_NRULES;            // [11]
+  double* s_tm = s_tp + PGN_NCODES;                          // [11]
+  double* s_warp0 = s_tm + PGN_NCODES;
+  const uint64_t* codes = P.point_code;
+  if constexpr (CODES_IN_SMEM) {
+    uint64_t* s_codes =
+      reinterpret_cast<uint64_t*>(s_warp0 + kWarpsPerBlock * per_warp_doubles<NDIM>());
+    for (int i = threadIdx.x; i < P.feval; i += blockDim.x)
+      s_codes[i] = __ldg(&P.point_code[i]);
+    codes = s_codes;
+  }
+  for (int i = threadIdx.x; i < PGN_NSETS * kWeightRow; i += blockDim.x) {
+    const int s = i / kWeightRow, r = i - s * kWeightRow;
+    s_w[i] = r < PGN_NRULES ? __ldg(&P.weights[s * PGN_NRULES + r]) : 0.0;
+  }
+  for (int i = threadIdx.x; i < PGN_NSETS * PGN_NRULES; i += blockDim.x) {
+    s_scale[i] = __ldg(&P.scale[i]);
+    s_norm[i] = __ldg(&P.norm[i]);
+  }
+  if (threadIdx.x < PGN_NCODES) {
+    s_tp[threadIdx.x] = P.half_plus_g[threadIdx.x];
+    s_tm[threadIdx.x] = P.half_minus_g[threadIdx.x];
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  double* s_x = s_warp0 + warp * per_warp_doubles<NDIM>();  // [NDIM][11]
+  double* s_f = s_x + NDIM * PGN_NCODES;                    // [64]
+  double* s_lo = s_f + 64;                                  // [NDIM]
+  double* s_up = s_lo + NDIM;                               // [NDIM]
+  double* s_ext = s_up + NDIM;                              // [NDIM]
+
+  // the functor: by value for empty/trivial ones, through a managed-memory copy otherwise
+  // (reference: cuda_copy_to_managed / make_gpu_integrand, cudaMemoryUtil.h:181-196, 345-353)
+  F* fptr;
+  if constexpr (BY_VALUE)
+    fptr = &fparam;
+  else
+    fptr = fparam;
+
+  const int feval = P.feval;
+  const int full_chunks = feval >> 6;  // chunks of 64 points in which every emulated thread works
+  const double jac = P.jacobian;
+  const double ratio = P.ratio;
+  const double one_minus_ratio = __dsub_rn(1.0, ratio);
+  const bool lo_half = lane < 16;
+
+  const size_t n = P.n;
+  const size_t stride = static_cast<size_t>(gridDim.x) * kWarpsPerBlock;
+  for (size_t reg = static_cast<size_t>(blockIdx.x) * kWarpsPerBlock + warp; reg < n; reg += stride) {
+    __syncwarp();
+    // ---- region bounds (INIT_REGION_POOL, Phases.cuh:323-349)
+    if (lane < NDIM) {
+      const double lo = P.left[static_cast<size_t>(lane) * n + reg];
+      const double up = __dadd_rn(lo, P.length[static_cast<size_t>(lane) * n + reg]);
+      s_lo[lane] = lo;
+      s_up[lane] = up;
+      s_ext[lane] = __dsub_rn(up, lo);
+    }
+    __syncwarp();
+    double vol = s_ext[0];
+#pragma unroll
+    for (int d = 1; d < NDIM; ++d)
+      vol = __dmul_rn(vol, s_ext[d]);
+    int max_dim;
+    {
+      double e = 0.0;
+      int idx = lane;
+      if (lane < NDIM) {
+        const double v = s_ext[lane];
+        e = v > 0.0 ? v : 0.0;
+      }
+      warp_argmax_first<kArgWidth>(e, idx);
+      max_dim = e > 0.0 ? idx : 0;
+    }
+    // ---- coordinate table: x(axis, code) with the reference's operation sequence
+    for (int e = lane; e < NDIM * PGN_NCODES; e += 32) {
+      const int d = e / PGN_NCODES;
+      const int c = e - d * PGN_NCODES;
+      const double inner = __fma_rn(s_tp[c], s_lo[d], __dmul_rn(s_tm[c], s_up[d]));
+      s_x[e] = __fma_rn(P.ranges[d], inner, P.lows[d]);
+    }
+    __syncwarp();
+
+    double sa[PGN_NRULES], sb[PGN_NRULES];
+#pragma unroll
+    for (int r = 0; r < PGN_NRULES; ++r)
+      sa[r] = sb[r] = 0.0;
+
+    auto eval_point = [&](int p, double (&sum)[PGN_NRULES], bool keep_f, int slot) {
+      const uint64_t code = codes[p];
+      double x[NDIM];
+#pragma unroll
+      for (int d = 0; d < NDIM; ++d)
+        x[d] = s_x[d * PGN_NCODES + static_cast<int>((code >> (4 * d)) & 0xF)];
+      const double fv = apply<F, NDIM>(*fptr, x);
+      const double fun = __dmul_rn(fv, jac);
+      if (keep_f)
+        s_f[slot] = fun;
+      const double* w = s_w + static_cast<int>(code >> 60) * kWeightRow;
+      const double2 w01 = *reinterpret_cast<const double2*>(w);
+      const double2 w23 = *reinterpret_cast<const double2*>(w + 2);
+      const double w4 = w[4];
+      sum[0] = __fma_rn(fun, w01.x, sum[0]);
+      sum[1] = __fma_rn(fun, w01.y, sum[1]);
+      sum[2] = __fma_rn(fun, w23.x, sum[2]);
+      sum[3] = __fma_rn(fun, w23.y, sum[3]);
+      sum[4] = __fma_rn(fun, w4, sum[4]);
+    };
+
+    // ---- chunk 0 keeps its function values for the fourth differences (Sample.cuh:176-219)
+    {
+      eval_point(lane, sa, true, lane);
+      if (lane + 32 < feval)
+        eval_point(lane + 32, sb, true, lane + 32);
+    }
+    // ---- full chunks: both emulated threads of every lane are busy
+    for (int k = 1; k < full_chunks; ++k) {
+      const int p = (k << 6) + lane;
+      eval_point(p, sa, false, 0);
+      eval_point(p + 32, sb, false, 0);
+    }
+    // ---- ragged tail (Sample.cuh:238-252)
+    if (full_chunks >= 1) {
+      const int p = (full_chunks << 6) + lane;
+      if (p < feval)
+        eval_point(p, sa, false, 0);
+      if (p + 32 < feval)
+        eval_point(p + 32, sb, false, 0);
+    }
+    __syncwarp();
+
+    // ---- split axis: first axis with the largest fourth difference (Sample.cuh:194-218)
+    int bisect;
+    {
+      double fd = 0.0;
+      int idx = lane;
+      if (lane < NDIM) {
+        const double f0 = s_f[0];
+        const double fp = s_f[1 + 2 * lane], fm = s_f[2 + 2 * lane];
+        const double gp = s_f[1 + 2 * lane + 2 * NDIM], gm = s_f[2 + 2 * lane + 2 * NDIM];
+        const double base = __dmul_rn(__dadd_rn(f0, f0), one_minus_ratio);
+        const double t = __fma_rn(ratio, __dadd_rn(fp, fm), base);
+        const double v = fabs(__dsub_rn(t, __dadd_rn(gp, gm)));
+        fd = v > 0.0 ? v : 0.0;
+      }
+      warp_argmax_first<kArgWidth>(fd, idx);
+      bisect = fd > 0.0 ? idx : max_dim;
+    }
+
+    // ---- the reference's block reduction (Sample.cuh:49-83) replayed inside one warp
+    double tot[PGN_NRULES];
+#pragma unroll
+    for (int r = 0; r < PGN_NRULES; ++r) {
+      const double keep = lo_half ? sa[r] : sb[r];
+      const double send = lo_half ? sb[r] : sa[r];
+      const double recv = __shfl_xor_sync(0xffffffffu, send, 16);
+      double v = __dadd_rn(keep, recv);  // lanes 0-15: A[i]+A[i+16]; lanes 16-31: B[i]+B[i+16]
+      v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, 8, 16));
+      v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, 4, 16));
+      v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, 2, 16));
+      v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, 1, 16));
+      tot[r] = __dadd_rn(__shfl_sync(0xffffffffu, v, 0), __shfl_sync(0xffffffffu, v, 16));
+    }
+
+    // ---- null-rule error (Sample.cuh:261-289): lane = 3*set + (rule-1)
+    double term = 0.0;
+    if (lane < 3 * PGN_NSETS) {
+      const int s = lane / 3;
+      const int k = lane - 3 * s;  // rule-1
+      const double a = k == 0 ? tot[1] : (k == 1 ? tot[2] : tot[3]);
+      const double b = k == 0 ? tot[2] : (k == 1 ? tot[3] : tot[4]);
+      term = __dmul_rn(fabs(__fma_rn(s_scale[s * PGN_NRULES + k + 1], a, b)),
+                       s_norm[s * PGN_NRULES + k + 1]);
+      term = fmax(0.0, term);
+    }
+    term = fmax(term, __shfl_down_sync(0xffffffffu, term, 12));
+    term = fmax(term, __shfl_down_sync(0xffffffffu, term, 6));
+    {
+      const double t3 = __shfl_down_sync(0xffffffffu, term, 3);
+      const double t6 = __shfl_down_sync(0xffffffffu, term, 6);
+      term = fmax(fmax(term, t3), t6);
+    }
+    const double e1 = __shfl_sync(0xffffffffu, term, 0);
+    const double e2 = __shfl_sync(0xffffffffu, term, 1);
+    const double e3 = __shfl_sync(0xffffffffu, term, 2);
+    if (lane == 0) {
+      const bool benign = (__dmul_rn(5.0, e1) <= e2) && (__dmul_rn(5.0, e2) <= e3);
+      const double inner = benign ? e1 : __dmul_rn(5.0, fmax(fmax(e1, e2), e3));
+      P.estimate[reg] = __dmul_rn(vol, tot[0]);
+      P.errorest[reg] = __dmul_rn(vol, inner);
+      P.axis[reg] = bisect;
+    }
+  }
+}
+
+template <typename F>
+struct pass_by_value
+  : std::integral_constant<bool, std::is_empty<F>::value && std::is_trivially_copyable<F>::value &&
+                                   std::is_default_constructible<F>::value> {};
+
+// One instantiation's launch logic (called through the pgn_eval_fn trampoline).
+template <typename F, int NDIM>
+int
+launch_evaluate(F* device_functor, const pgn_region_view* v)
+{
+  constexpr bool kByValue = pass_by_value<F>::value;
+  if (v == nullptr || v->rule.ndim != NDIM)
+    return PGN_ERR_INVALID;
+  if (v->n == 0)
+    return PGN_OK;
+  EvalParams P;
+  P.left = v->left;
+  P.length = v->length;
+  P.n = v->n;
+  P.estimate = v->estimate;
+  P.errorest = v->errorest;
+  P.axis = v->axis;
+  P.point_code = v->rule.point_code;
+  P.weights = v->rule.weights;
+  P.scale = v->rule.scale;
+  P.norm = v->rule.norm;
+  for (int d = 0; d <= PGN_MAX_NDIM; ++d) {
+    P.lows[d] = v->lows[d];
+    P.ranges[d] = v->ranges[d];
+  }
+  for (int c = 0; c < PGN_NCODES; ++c) {
+    P.half_plus_g[c] = v->rule.half_plus_g[c];
+    P.half_minus_g[c] = v->rule.half_minus_g[c];
+  }
+  P.jacobian = v->jacobian;
+  P.ratio = v->rule.ratio;
+  P.feval = v->rule.feval;
+
+  const bool codes_in_smem = smem_bytes<NDIM>(P.feval, true) <= 100 * 1024;
+  const size_t smem = smem_bytes<NDIM>(P.feval, codes_in_smem);
+  cudaStream_t stream = static_cast<cudaStream_t>(v->stream);
+
+  auto launch = [&](auto kernel) -> int {
+    static int blocks_per_sm = 0;  // per instantiation (the lambda is instantiated per kernel)
+    static size_t configured_smem = 0;
+    if (smem > configured_smem) {
+      if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem)) != cudaSuccess)
+        return PGN_ERR_CUDA;
+      configured_smem = smem;
+      blocks_per_sm = 0;
+    }
+    if (blocks_per_sm == 0) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kWarpsPerBlock * 32,
+                                                        smem) != cudaSuccess ||
+          blocks_per_sm < 1)
+        return PGN_ERR_CUDA;
+    }
+    const size_t want = (v->n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const size_t cap = static_cast<size_t>(v->sm_count > 0 ? v->sm_count : 148) * blocks_per_sm;
+    const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
+    if constexpr (kByValue)
+      kernel<<<grid, kWarpsPerBlock * 32, smem, stream>>>(F{}, P);
+    else
+      kernel<<<grid, kWarpsPerBlock * 32, smem, stream>>>(device_functor, P);
+    return cudaGetLastError() == cudaSuccess ? PGN_OK : PGN_ERR_CUDA;
+  };
+  if (codes_in_smem)
+    return launch(evaluate_kernel<F, NDIM, kByValue, true>);
+  return launch(evaluate_kernel<F, NDIM, kByValue, false>);
+}
+
+template <typename F, int NDIM>
+int
+trampoline(void* user, const pgn_region_view* v)
+{
+  return launch_evaluate<F, NDIM>(static_cast<F*>(user), v);
+}
+
+}  // namespace detail
+
+// Owns the device-visible copy of a functor for the duration of one integrate call.
+// Mirrors quad::cuda_copy_to_managed (copy-construct into managed memory) and the explicit
+// destructor call + cudaFree at the end of Workspace::integrate (Workspace.cuh:451-452).
+template <typename F, int NDIM>
+class Evaluator {
+public:
+  explicit Evaluator(const F& f)
+  {
+    if constexpr (!detail::pass_by_value<F>::value) {
+      void* mem = nullptr;
+      if (cudaMallocManaged(&mem, sizeof(F)) != cudaSuccess)
+        throw std::bad_alloc();
+      copy_ = new (mem) F(f);
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaMemPrefetchAsync(copy_, sizeof(F), dev, 0);
+    }
+  }
+  ~Evaluator()
+  {
+    if (copy_ != nullptr) {
+      cudaDeviceSynchronize();
+      copy_->~F();
+      cudaFree(copy_);
+    }
+  }
+  Evaluator(const Evaluator&) = delete;
+  Evaluator& operator=(const Evaluator&) = delete;
+
+  pgn_eval_fn fn() const { return &detail::trampoline<F, NDIM>; }
+  void* user() const { return copy_; }
+
+private:
+  F* copy_ = nullptr;
+};
+
+}  // namespace pagani_b200
+#endif

@@ -1,0 +1,208 @@
+// The six Genz test-integrand families in the parameterisation the reference benchmarks use
+// (common/cuda/integrands.cuh:1303-1932: F_1 oscillatory, F_2 product peak, F_3 corner peak,
+// F_4 Gaussian, F_5 C0, F_6 discontinuous at 5..8 dimensions) plus the 10-dimensional F_5/F_6
+// this project adds for BASELINE config 4.
+//
+// Every functor is a stateless callable taking ndim doubles.  The floating-point expression trees
+// (association order, literal constants, pow(x, 2.) kept as a genuine pow call) are those of the
+// mathematical definitions as the reference writes them, because region-trajectory parity needs
+// f(x) bit-identical: symmetric integrands tie their fourth differences and rounding decides the
+// split axis.  tests/ pin this against the reference binary on the GPU.
+//
+// The same header is compiled into the reference oracle harness (oracle/ref/ref_pagani.cu) for the
+// 10-D functors the reference does not define.
+#ifndef PAGANI_B200_GENZ_CUH
+#define PAGANI_B200_GENZ_CUH
+
+#include <cmath>
+
+#ifdef __CUDACC__
+#define PGN_HD __host__ __device__
+#else
+#define PGN_HD
+#endif
+
+namespace pagani_b200 {
+namespace genz {
+
+// F_1: cos(x0 + 2 x1 + 3 x2 + ...)
+template <int N>
+struct Oscillatory {
+  static constexpr int ndim = N;
+  template <class... T>
+  PGN_HD double
+  operator()(T... xs) const
+  {
+    static_assert(sizeof...(T) == N, "arity");
+    const double x[N] = {xs...};
+    double s = x[0];
+#pragma unroll
+    for (int k = 1; k < N; ++k)
+      s = s + static_cast<double>(k + 1) * x[k];
+    return cos(s);
+  }
+};
+
+// F_2: prod_k 1 / (a^-2 + (x_k - b)^2),  a = 50, b = .5
+template <int N>
+struct ProductPeak {
+  static constexpr int ndim = N;
+  template <class... T>
+  PGN_HD double
+  operator()(T... xs) const
+  {
+    static_assert(sizeof...(T) == N, "arity");
+    const double x[N] = {xs...};
+    const double a = 50.;
+    const double b = .5;
+    double val = 1. / ((1. / pow(a, 2.)) + pow(x[0] - b, 2.));
+#pragma unroll
+    for (int k = 1; k < N; ++k) {
+      const double term = 1. / ((1. / pow(a, 2.)) + pow(x[k] - b, 2.));
+      val = val * term;
+    }
+    return val;
+  }
+};
+
+// F_3: (1 + N x_{N-1} + ... + 4 x_3 + 3 x_0 + 2 x_1 + x_2)^-(N+1)
+template <int N>
+struct CornerPeak {
+  static constexpr int ndim = N;
+  template <class... T>
+  PGN_HD double
+  operator()(T... xs) const
+  {
+    static_assert(sizeof...(T) == N && N >= 4, "arity");
+    const double x[N] = {xs...};
+    double s = 1.;
+#pragma unroll
+    for (int c = N; c >= 4; --c)
+      s = s + static_cast<double>(c) * x[c - 1];
+    s = s + 3. * x[0];
+    s = s + 2. * x[1];
+    s = s + x[2];
+    return pow(s, -static_cast<double>(N + 1));
+  }
+};
+
+// F_4: exp(-sum_k 25^2 (x_k - .5)^2)
+template <int N>
+struct Gaussian {
+  static constexpr int ndim = N;
+  template <class... T>
+  PGN_HD double
+  operator()(T... xs) const
+  {
+    static_assert(sizeof...(T) == N, "arity");
+    const double x[N] = {xs...};
+    const double beta = .5;
+    double s = pow(25., 2.) * pow(x[0] - beta, 2.);
+#pragma unroll
+    for (int k = 1; k < N; ++k)
+      s = s + pow(25., 2.) * pow(x[k] - beta, 2.);
+    return exp(-1.0 * s);
+  }
+};
+
+// F_5: exp(-10 sum_k |x_k - .5|)
+template <int N>
+struct CZero {
+  static constexpr int ndim = N;
+  template <class... T>
+  PGN_HD double
+  operator()(T... xs) const
+  {
+    static_assert(sizeof...(T) == N, "arity");
+    const double x[N] = {xs...};
+    const double beta = .5;
+    double t1 = -10. * fabs(x[0] - beta);
+#pragma unroll
+    for (int k = 1; k < N; ++k)
+      t1 = t1 - 10. * fabs(x[k] - beta);
+    return exp(t1);
+  }
+};
+
+// F_6: 0 if any x_k > beta_k, else exp(sum alpha_k x_k).  The reference orders its arguments
+// differently at every dimension; the tables below give, per argument, its threshold and its
+// coefficient, and `Descending` says whether the exponent is summed from the last argument down
+// (8-D, 10-D) or from the first up (5..7-D).
+template <int N>
+struct DiscontinuousSpec;
+template <>
+struct DiscontinuousSpec<5> {
+  static constexpr bool descending = false;
+  PGN_HD static double beta(int i) { constexpr double b[5] = {.8, .7, .6, .5, .4}; return b[i]; }
+  PGN_HD static double alpha(int i) { constexpr double a[5] = {9., 8., 7., 6., 5.}; return a[i]; }
+};
+template <>
+struct DiscontinuousSpec<6> {
+  static constexpr bool descending = false;
+  PGN_HD static double beta(int i) { constexpr double b[6] = {.9, .8, .7, .6, .5, .4}; return b[i]; }
+  PGN_HD static double alpha(int i) { constexpr double a[6] = {10., 9., 8., 7., 6., 5.}; return a[i]; }
+};
+template <>
+struct DiscontinuousSpec<7> {
+  static constexpr bool descending = false;
+  PGN_HD static double beta(int i) { constexpr double b[7] = {.9, .8, .7, .6, .5, .4, .3}; return b[i]; }
+  PGN_HD static double alpha(int i) { constexpr double a[7] = {10., 9., 8., 7., 6., 5., 4.}; return a[i]; }
+};
+template <>
+struct DiscontinuousSpec<8> {
+  static constexpr bool descending = true;
+  PGN_HD static double beta(int i) { constexpr double b[8] = {.2, .3, .4, .5, .6, .7, .8, .9}; return b[i]; }
+  PGN_HD static double alpha(int i) { constexpr double a[8] = {3., 4., 5., 6., 7., 8., 9., 10.}; return a[i]; }
+};
+// our 10-D extension: the literal pattern would reach beta = 0, so the ends are
+// squeezed to .15 and .95 instead.
+template <>
+struct DiscontinuousSpec<10> {
+  static constexpr bool descending = true;
+  PGN_HD static double beta(int i)
+  {
+    constexpr double b[10] = {.15, .2, .3, .4, .5, .6, .7, .8, .9, .95};
+    return b[i];
+  }
+  PGN_HD static double alpha(int i)
+  {
+    constexpr double a[10] = {2., 3., 4., 5., 6., 7., 8., 9., 10., 11.};
+    return a[i];
+  }
+};
+
+template <int N>
+struct Discontinuous {
+  static constexpr int ndim = N;
+  using Spec = DiscontinuousSpec<N>;
+  template <class... T>
+  PGN_HD double
+  operator()(T... xs) const
+  {
+    static_assert(sizeof...(T) == N, "arity");
+    const double x[N] = {xs...};
+    bool outside = false;
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      outside = outside || (x[k] > Spec::beta(k));
+    if (outside)
+      return 0.;
+    double s;
+    if (Spec::descending) {
+      s = Spec::alpha(N - 1) * x[N - 1];
+#pragma unroll
+      for (int k = N - 2; k >= 0; --k)
+        s = s + Spec::alpha(k) * x[k];
+    } else {
+      s = Spec::alpha(0) * x[0];
+#pragma unroll
+      for (int k = 1; k < N; ++k)
+        s = s + Spec::alpha(k) * x[k];
+    }
+    return exp(s);
+  }
+};
+
+}  // namespace genz
+}  // namespace pagani_b200
+#endif
