@@ -151,6 +151,9 @@ SIGNATURES = {
     "pgn_last_error": (C.c_char_p, []),
     "pgn_version": (C.c_char_p, []),
     "pgn_device_info": (C.c_int, [_vp, _P(C.c_int), _P(C.c_size_t), _P(C.c_size_t)]),
+    "pgn_set_eval_variant": (C.c_int, [_vp, C.c_int]),
+    "pgn_get_stream": (C.c_int, [_vp, _P(_vp)]),
+    "pgn_launch_count": (C.c_int, [_vp, _P(C.c_uint64)]),
     "pgn_feval": (C.c_int, [C.c_int]),
     "pgn_rule_tables_host": (C.c_int, [C.c_int, _dp, _dp, _dp, _dp, _P(C.c_int32), _P(C.c_uint64)]),
     "pgn_rule_view_get": (C.c_int, [_vp, _P(pgn_rule_view)]),

@@ -44,6 +44,9 @@ const GenzEntry kGenz[] = {
   entry<genz::CZero<7>>(5),         entry<genz::CZero<8>>(5),         entry<genz::CZero<10>>(5),
   entry<genz::Discontinuous<5>>(6), entry<genz::Discontinuous<6>>(6), entry<genz::Discontinuous<7>>(6),
   entry<genz::Discontinuous<8>>(6), entry<genz::Discontinuous<10>>(6),
+  // the reference unit tests' integrands: family 0 constant, 7 product of coordinates, 8 NaN
+  entry<testfn::Constant<2>>(0),    entry<testfn::Constant<3>>(0),    entry<testfn::Constant<5>>(0),
+  entry<testfn::Constant<8>>(0),    entry<testfn::Product<2>>(7),     entry<testfn::NotANumber<2>>(8),
 };
 
 const GenzEntry*
@@ -113,6 +116,33 @@ int
 pgn_device_info(pgn_ctx* ctx, int* sm_count, size_t* free_bytes, size_t* total_bytes)
 {
   return ctx ? ctx->engine.device_info(sm_count, free_bytes, total_bytes) : PGN_ERR_INVALID;
+}
+
+int
+pgn_set_eval_variant(pgn_ctx* ctx, int variant)
+{
+  if (!ctx || variant < 0 || variant > 2)
+    return PGN_ERR_INVALID;
+  ctx->engine.set_eval_variant(variant);
+  return PGN_OK;
+}
+
+int
+pgn_get_stream(pgn_ctx* ctx, void** stream)
+{
+  if (!ctx || !stream)
+    return PGN_ERR_INVALID;
+  *stream = ctx->engine.stream();
+  return PGN_OK;
+}
+
+int
+pgn_launch_count(pgn_ctx* ctx, uint64_t* launches)
+{
+  if (!ctx || !launches)
+    return PGN_ERR_INVALID;
+  *launches = ctx->engine.launches();
+  return PGN_OK;
 }
 
 int
@@ -292,6 +322,10 @@ pgn_genz_true_value(int family, int ndim)
   const double pi = 3.14159265358979323846;
   double v = 1.0;
   switch (family) {
+    case 0:
+      return 15.37;
+    case 7:
+      return std::pow(.5, ndim);
     case 1: {
       // Re prod_k (e^{i k} - 1) / (i k)
       double re = 1.0, im = 0.0;

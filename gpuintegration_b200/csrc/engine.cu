@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -294,6 +295,8 @@ Engine::init()
   PGN_CUDA(cudaMallocHost(&host_local_, sizeof(double) * kHostStats));
   PGN_CUDA(cudaMallocHost(&host_global_, sizeof(double) * kHostStats));
   rank_counts_.assign(1, 0);
+  if (const char* ev = std::getenv("PGN_EVAL_VARIANT"))
+    eval_variant_ = std::atoi(ev);
   ready_ = true;
   return PGN_OK;
 }
@@ -396,7 +399,7 @@ Engine::regions_init_uniform(int parts)
   PGN_TRY(length_[cur_].reserve(sizeof(double) * std::max<size_t>(n, 1) * ndim_));
   if (w == 1) {
     if (n > 0)
-      k_uniform_split<<<blocks_for(n, 512), 512, 0, stream_>>>(
+      ++launches_, k_uniform_split<<<blocks_for(n, 512), 512, 0, stream_>>>(
         left_[cur_].as<double>(), length_[cur_].as<double>(), n, parts, ndim_, edge);
     PGN_CUDA(cudaGetLastError());
   } else {
@@ -487,6 +490,8 @@ Engine::launch_evaluate(pgn_eval_fn fn, void* user)
   rule_view(&v.rule);
   v.stream = stream_;
   v.sm_count = sm_count_;
+  v.reserved = eval_variant_;
+  ++launches_;
   const int rc = fn(user, &v);
   if (rc != PGN_OK) {
     cudaError_t e = cudaGetLastError();
@@ -556,12 +561,12 @@ Engine::run_classify(double epsrel, int relerr)
     PGN_TRY(write_empty_stats(stats_dev_.as<double>(), stream_));
     err_cur_ = err_raw_.as<double>();
   } else if (parents_n_ > 0) {
-    k_classify<true><<<tiles_for(n_), kBlock, 0, stream_>>>(
+    ++launches_, k_classify<true><<<tiles_for(n_), kBlock, 0, stream_>>>(
       est_.as<double>(), err_raw_.as<double>(), par_est_[par_cur_].as<double>(),
       err_ref_.as<double>(), active_.as<uint8_t>(), n_, epsrel, relerr, ts);
     err_cur_ = err_ref_.as<double>();
   } else {
-    k_classify<false><<<tiles_for(n_), kBlock, 0, stream_>>>(
+    ++launches_, k_classify<false><<<tiles_for(n_), kBlock, 0, stream_>>>(
       est_.as<double>(), err_raw_.as<double>(), nullptr, nullptr, active_.as<uint8_t>(), n_, epsrel,
       relerr, ts);
     err_cur_ = err_raw_.as<double>();
@@ -581,13 +586,13 @@ Engine::run_threshold(int mode, double threshold)
     return write_empty_stats(stats_dev_.as<double>(), stream_);
   const int tiles = tiles_for(n_);
   if (mode == 0)
-    k_threshold<0><<<tiles, kBlock, 0, stream_>>>(est_.as<double>(), err_cur_, active_.as<uint8_t>(),
+    ++launches_, k_threshold<0><<<tiles, kBlock, 0, stream_>>>(est_.as<double>(), err_cur_, active_.as<uint8_t>(),
                                                   n_, threshold, ts);
   else if (mode == 1)
-    k_threshold<1><<<tiles, kBlock, 0, stream_>>>(est_.as<double>(), err_cur_, active_.as<uint8_t>(),
+    ++launches_, k_threshold<1><<<tiles, kBlock, 0, stream_>>>(est_.as<double>(), err_cur_, active_.as<uint8_t>(),
                                                   n_, threshold, ts);
   else
-    k_threshold<2><<<tiles, kBlock, 0, stream_>>>(est_.as<double>(), err_cur_, active_.as<uint8_t>(),
+    ++launches_, k_threshold<2><<<tiles, kBlock, 0, stream_>>>(est_.as<double>(), err_cur_, active_.as<uint8_t>(),
                                                   n_, threshold, ts);
   PGN_CUDA(cudaGetLastError());
   return PGN_OK;
@@ -601,7 +606,7 @@ Engine::run_recount()
                  comm_ ? comm_->nranks : 1};
   if (n_ == 0)
     return write_empty_stats(stats_dev_.as<double>(), stream_);
-  k_recount<<<tiles_for(n_), kBlock, 0, stream_>>>(est_.as<double>(), err_cur_,
+  ++launches_, k_recount<<<tiles_for(n_), kBlock, 0, stream_>>>(est_.as<double>(), err_cur_,
                                                    active_.as<uint8_t>(), n_, ts);
   PGN_CUDA(cudaGetLastError());
   return PGN_OK;
@@ -615,11 +620,11 @@ Engine::digest_device(const void* p, size_t elem, size_t n)
   if (n > 0) {
     const unsigned g = blocks_for(n, 256);
     if (elem == 8)
-      k_digest<double><<<g, 256, 0, stream_>>>(static_cast<const double*>(p), n, out);
+      ++launches_, k_digest<double><<<g, 256, 0, stream_>>>(static_cast<const double*>(p), n, out);
     else if (elem == 4)
-      k_digest<int32_t><<<g, 256, 0, stream_>>>(static_cast<const int32_t*>(p), n, out);
+      ++launches_, k_digest<int32_t><<<g, 256, 0, stream_>>>(static_cast<const int32_t*>(p), n, out);
     else
-      k_digest<uint8_t><<<g, 256, 0, stream_>>>(static_cast<const uint8_t*>(p), n, out);
+      ++launches_, k_digest<uint8_t><<<g, 256, 0, stream_>>>(static_cast<const uint8_t*>(p), n, out);
   }
   unsigned long long h = 0;
   cudaMemcpyAsync(&h, out, sizeof h, cudaMemcpyDeviceToHost, stream_);
@@ -823,7 +828,7 @@ Engine::filter(size_t* num_active)
   A.parent_err = par_err_[pn].as<double>();
   A.out_axis = par_axis_.as<int32_t>();
   A.ndim = ndim_;
-  k_compact<false><<<tiles_for(n_), kBlock, 0, stream_>>>(A);
+  ++launches_, k_compact<false><<<tiles_for(n_), kBlock, 0, stream_>>>(A);
   PGN_CUDA(cudaGetLastError());
   cur_ = nxt;
   par_cur_ = pn;
@@ -841,17 +846,23 @@ Engine::split()
   PGN_CUDA(cudaSetDevice(device_));
   if (n_ == 0)
     return PGN_OK;
-  if (!filtered_pending_) {
-    set_last_error("split() needs filter() first (it consumes the compacted split axes)");
+  // after filter() the compacted axes are used; without it (RegionSplitting.cu sets the axes by
+  // hand and splits every region) the per-region axes of the current list
+  if (!filtered_pending_ && !evaluated_) {
+    set_last_error("split() needs split axes: evaluate(), set_estimates() or filter() first");
     return PGN_ERR_STATE;
   }
+  const int32_t* axes = filtered_pending_ ? par_axis_.as<int32_t>() : axis_.as<int32_t>();
   const size_t m = n_;
   const int nxt = 1 - cur_;
   PGN_TRY(left_[nxt].reserve(sizeof(double) * 2 * m * ndim_));
   PGN_TRY(length_[nxt].reserve(sizeof(double) * 2 * m * ndim_));
-  k_split<<<blocks_for(m, kBlock), kBlock, 0, stream_>>>(
-    left_[cur_].as<double>(), length_[cur_].as<double>(), par_axis_.as<int32_t>(), m, ndim_,
+  ++launches_, k_split<<<blocks_for(m, kBlock), kBlock, 0, stream_>>>(
+    left_[cur_].as<double>(), length_[cur_].as<double>(), axes, m, ndim_,
     left_[nxt].as<double>(), length_[nxt].as<double>());
+  if (!filtered_pending_)
+    parents_n_ = 0;
+  evaluated_ = classified_ = false;
   PGN_CUDA(cudaGetLastError());
   cur_ = nxt;
   n_ = 2 * m;
@@ -893,7 +904,7 @@ Engine::rebalance_parents(size_t* m_local)
       continue;
     // self transfers are packed straight into the receive staging area
     double* dst = t.dst == me ? pack_recv_.as<double>() + roff[k] : pack_send_.as<double>() + soff[k];
-    k_pack<<<blocks_for(t.count * cols, 256), 256, 0, stream_>>>(
+    ++launches_, k_pack<<<blocks_for(t.count * cols, 256), 256, 0, stream_>>>(
       left_[cur_].as<double>(), length_[cur_].as<double>(), par_est_[pc].as<double>(),
       par_err_[pc].as<double>(), par_axis_.as<int32_t>(), m_old, ndim_, t.src_offset, t.count, dst);
   }
@@ -914,7 +925,7 @@ Engine::rebalance_parents(size_t* m_local)
     const Transfer& t = plan[k];
     if (t.dst != me)
       continue;
-    k_unpack<<<blocks_for(t.count * cols, 256), 256, 0, stream_>>>(
+    ++launches_, k_unpack<<<blocks_for(t.count * cols, 256), 256, 0, stream_>>>(
       pack_recv_.as<double>() + roff[k], t.count, t.dst_offset, m_new, ndim_,
       left_[nxt].as<double>(), length_[nxt].as<double>(), par_est_[pn].as<double>(),
       par_err_[pn].as<double>(), new_axis.as<int32_t>());
@@ -966,7 +977,7 @@ Engine::compact_and_split(size_t m_local, size_t m_global, bool* rebalanced)
     A.out_length = length_[nxt].as<double>();
     A.out_axis = nullptr;
     if (n_ > 0 && m_local > 0)
-      k_compact<true><<<tiles_for(n_), kBlock, 0, stream_>>>(A);
+      ++launches_, k_compact<true><<<tiles_for(n_), kBlock, 0, stream_>>>(A);
     PGN_CUDA(cudaGetLastError());
     cur_ = nxt;
     par_cur_ = pn;
@@ -982,7 +993,7 @@ Engine::compact_and_split(size_t m_local, size_t m_global, bool* rebalanced)
   A.out_length = length_[nxt].as<double>();
   A.out_axis = par_axis_.as<int32_t>();
   if (n_ > 0 && m_local > 0)
-    k_compact<false><<<tiles_for(n_), kBlock, 0, stream_>>>(A);
+    ++launches_, k_compact<false><<<tiles_for(n_), kBlock, 0, stream_>>>(A);
   PGN_CUDA(cudaGetLastError());
   cur_ = nxt;
   par_cur_ = pn;
@@ -994,7 +1005,7 @@ Engine::compact_and_split(size_t m_local, size_t m_global, bool* rebalanced)
   PGN_TRY(left_[nx2].reserve(sizeof(double) * 2 * m2 * ndim_));
   PGN_TRY(length_[nx2].reserve(sizeof(double) * 2 * m2 * ndim_));
   if (m > 0)
-    k_split<<<blocks_for(m, kBlock), kBlock, 0, stream_>>>(
+    ++launches_, k_split<<<blocks_for(m, kBlock), kBlock, 0, stream_>>>(
       left_[cur_].as<double>(), length_[cur_].as<double>(), par_axis_.as<int32_t>(), m, ndim_,
       left_[nx2].as<double>(), length_[nx2].as<double>());
   PGN_CUDA(cudaGetLastError());
@@ -1262,6 +1273,8 @@ Engine::integrate(pgn_eval_fn fn, void* user, const pgn_integrate_args& args, pg
       m_local = static_cast<size_t>(host_local_[kNumActive]);
       counts = rank_counts_;
       st.budget_overflow = 1;
+      if (opts_.trace_arrays)
+        st.dig_active = digest_device(active_.ptr, 1, n_);
     }
 
     HeuristicOutcome hs;

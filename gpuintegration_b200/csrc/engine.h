@@ -78,12 +78,14 @@ public:
   int comm_init_nccl(const uint8_t* id, int nranks, int rank);
   int comm_init_host(int nranks, int rank, pgn_allreduce_fn ar, pgn_alltoallv_fn a2a, void* user);
   int comm_size(int* nranks, int* rank) const;
+  void set_eval_variant(int v) { eval_variant_ = v; }
   void set_rebalance(double max_over_mean, size_t min_regions)
   {
     rebalance_ratio_ = max_over_mean;
     rebalance_min_ = min_regions;
   }
 
+  uint64_t launches() const { return launches_; }
   const std::vector<pgn_iter_stats>& trace() const { return trace_; }
   cudaStream_t stream() const { return stream_; }
 
@@ -121,6 +123,7 @@ private:
   pgn_opts opts_;
   int device_ = 0;
   int sm_count_ = 148;
+  int eval_variant_ = 0;  // pgn_region_view::reserved: 0 default, 1 shift/mask, 2 byte-permute
   cudaStream_t stream_ = nullptr;
   bool ready_ = false;
 
@@ -160,6 +163,7 @@ private:
   double rebalance_ratio_ = 1.10;
   size_t rebalance_min_ = 4096;
 
+  uint64_t launches_ = 0;  // kernels of this library enqueued so far (bench.py's gpu_launches)
   std::vector<pgn_iter_stats> trace_;
   cudaEvent_t ev_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };

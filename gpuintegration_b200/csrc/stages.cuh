@@ -290,6 +290,8 @@ k_threshold(const double* __restrict__ est, const double* __restrict__ err, uint
       const double flag = (MODE == 2) ? 1.0 : ((e > threshold) ? 1.0 : 0.0);
       a.v[kSumActErr] += flag * e;
       a.v[kNumActive] += flag;
+      a.mn = fmin(a.mn, e);  // the threshold search reads min/max of the errors after a MODE 2 pass
+      a.mx = fmax(a.mx, e);
       if (MODE != 0) {
         const double v = est[i];
         a.v[kSumActEst] += flag * v;

@@ -311,6 +311,23 @@ class Workspace:
         self._keep += [ar, a2a]
         capi.check(self._lib.pgn_comm_set_host_collective(self._ctx, nranks, rank, ar, a2a, None), "pgn_comm_set_host_collective")
 
+    @property
+    def cuda_stream(self):
+        """Raw cudaStream_t of the engine (wrap with torch.cuda.ExternalStream for event timing)."""
+        s = C.c_void_p()
+        capi.check(self._lib.pgn_get_stream(self._ctx, C.byref(s)), "pgn_get_stream")
+        return s.value or 0
+
+    @property
+    def launch_count(self):
+        n = C.c_uint64()
+        capi.check(self._lib.pgn_launch_count(self._ctx, C.byref(n)), "pgn_launch_count")
+        return n.value
+
+    def set_eval_variant(self, variant):
+        """0 default, 1 shift/mask point loop, 2 byte-permute point loop (bit-identical results)."""
+        capi.check(self._lib.pgn_set_eval_variant(self._ctx, variant), "pgn_set_eval_variant")
+
     def set_rebalance(self, max_over_mean=1.10, min_regions=4096):
         capi.check(self._lib.pgn_set_rebalance(self._ctx, max_over_mean, min_regions), "pgn_set_rebalance")
 

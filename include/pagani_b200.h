@@ -133,6 +133,13 @@ void pgn_destroy(pgn_ctx* ctx);                                /* ~Cubature_rule
 const char* pgn_last_error(void);
 const char* pgn_version(void);
 int pgn_device_info(pgn_ctx* ctx, int* sm_count, size_t* free_bytes, size_t* total_bytes);
+/* Which point-loop variant the pre-instantiated evaluators launch (they must agree bit for bit):
+ * 0 default, 1 shift/mask addressing, 2 byte-permute addressing.  Also env PGN_EVAL_VARIANT. */
+int pgn_set_eval_variant(pgn_ctx* ctx, int variant);
+/* The context's private cudaStream_t (for event timing by the caller) and the number of kernels of
+ * this library it has enqueued so far. */
+int pgn_get_stream(pgn_ctx* ctx, void** stream);
+int pgn_launch_count(pgn_ctx* ctx, uint64_t* launches);
 
 /* ---- rule tables (golden-vector access; Rule.cuh) ------------------------------------------- */
 int pgn_feval(int ndim); /* pagani::CuhreFuncEvalsPerRegion, quad.h:68-75 */

@@ -10,15 +10,23 @@
 //    the two warp results.  Here ONE WARP owns a region and every lane plays reference threads
 //    `lane` (accumulator set A) and `lane+32` (set B): the same per-thread chains, the same tree
 //    (A and B are reduced in the two half-warps after one xor-16 exchange), the same final A+B.
-//    No __syncthreads, no thread-0 serial sections, two independent integrand evaluations in
-//    flight per lane to keep the FP64 pipe fed.
+//    No __syncthreads, no thread-0 serial sections.
 //  * The affine map region->integration volume is evaluated with the reference's exact operation
 //    sequence (x = fma(range, fma(.5+g, lo, (.5-g)*hi), low); checked against its PTX) but only
 //    once per (axis, generator value): a coordinate can take just 11 values per axis, so each warp
-//    builds an 11 x ndim table in shared memory per region and a point becomes ndim table look-ups
-//    driven by one packed 4-bit-per-axis code word (staged in shared memory with the weights).
+//    builds an 11 x ndim table in shared memory per region and a point becomes ndim table look-ups.
 //  * Fourth differences (split axis) and the 27 null-rule terms are computed lane-parallel; max and
 //    first-wins argmax are order independent, so this does not change results.
+//
+// Two variants of the point loop exist and must agree bit for bit (tests/test_gpu_parity.py):
+//   evaluate_kernel     look-ups addressed with shifts/masks from a 4-bit-per-axis code word;
+//   evaluate_kernel_bp  ("byte permute", the default for ndim <= 12): the code word of a point holds
+//                       one BYTE per axis = 8 x its coordinate code, the per-warp table and the weight
+//                       table sit on 256-byte boundaries, and a shared-memory address is formed by ONE
+//                       PRMT that splices that byte under the table base; the axis offset is the
+//                       immediate of the LDS.  1 ALU + 1 LDS per coordinate instead of 3 ALU + 1 LDS:
+//                       for cheap integrands the kernel is issue-bound, not FP64-bound, so integer
+//                       instructions are what there is to save.
 //
 // Persistent launch: grid = SMs x resident blocks, warps stride over the region list.
 #ifndef PAGANI_B200_EVALUATE_CUH
@@ -38,6 +46,9 @@ namespace pagani_b200 {
 
 constexpr int kWarpsPerBlock = 4;
 constexpr int kWeightRow = 6;  // 5 rule weights padded to 48 B so a row is three 16-byte loads
+
+// values of pgn_region_view::reserved
+enum EvalVariant { kVariantDefault = 0, kVariantShift = 1, kVariantBytePermute = 2 };
 
 namespace detail {
 
@@ -76,21 +87,32 @@ struct EvalParams {
   int feval;
 };
 
-template <int NDIM>
-__host__ __device__ constexpr int
-per_warp_doubles()
-{
-  // coordinate table, first-chunk function values, lower, upper, extent
-  return NDIM * PGN_NCODES + 64 + 3 * NDIM;
-}
+// How the functor reaches the kernel: small trivially-copyable functors travel by value in the
+// kernel's constant parameter space (state reads cost nothing); anything else is read through a
+// copy-constructed object in managed memory, as the reference does for every functor
+// (cuda_copy_to_managed, common/cuda/cudaMemoryUtil.h:181-196).
+template <typename F>
+struct pass_by_value
+  : std::integral_constant<bool, std::is_trivially_copyable<F>::value && (sizeof(F) <= 2048)> {};
 
-template <int NDIM>
-__host__ __device__ constexpr size_t
-smem_bytes(int feval, bool codes_in_smem)
+template <typename F, bool BY_VALUE>
+struct FunctorArg;
+template <typename F>
+struct FunctorArg<F, true> {
+  F f;
+  // the reference's functors have non-const call operators; they do not write to themselves
+  __device__ __forceinline__ F* get() const { return const_cast<F*>(&f); }
+};
+template <typename F>
+struct FunctorArg<F, false> {
+  F* p;
+  __device__ __forceinline__ F* get() const { return p; }
+};
+
+__host__ __device__ constexpr int
+feval_of(int n)
 {
-  return sizeof(double) * (PGN_NSETS * kWeightRow + 2 * PGN_NSETS * PGN_NRULES + 2 * PGN_NCODES +
-                           kWarpsPerBlock * per_warp_doubles<NDIM>()) +
-         (codes_in_smem ? sizeof(uint64_t) * static_cast<size_t>(feval) : 0);
+  return 1 + 8 * n + 6 * n * (n - 1) + 4 * n * (n - 1) * (n - 2) / 3 + (1 << n);
 }
 
 // first-wins arg-max over lanes (value v >= 0, index idx); ties go to the smaller index
@@ -109,12 +131,141 @@ warp_argmax_first(double& v, int& idx)
   }
 }
 
+// ---- per-region prologue: bounds, volume, default axis, coordinate table -------------------------
+// (INIT_REGION_POOL, Phases.cuh:323-349, and the affine map of computePermutation, Sample.cuh:124-131)
+template <int NDIM>
+__device__ __forceinline__ void
+region_prologue(const EvalParams& P, size_t reg, int lane, const double* s_tp, const double* s_tm,
+                double* s_lo, double* s_up, double* s_ext, double* s_x, double& vol, int& max_dim)
+{
+  constexpr int kArgWidth = NDIM <= 16 ? 16 : 32;
+  const size_t n = P.n;
+  if (lane < NDIM) {
+    const double lo = P.left[static_cast<size_t>(lane) * n + reg];
+    const double up = __dadd_rn(lo, P.length[static_cast<size_t>(lane) * n + reg]);
+    s_lo[lane] = lo;
+    s_up[lane] = up;
+    s_ext[lane] = __dsub_rn(up, lo);
+  }
+  __syncwarp();
+  vol = s_ext[0];
+#pragma unroll
+  for (int d = 1; d < NDIM; ++d)
+    vol = __dmul_rn(vol, s_ext[d]);
+  {
+    double e = 0.0;
+    int idx = lane;
+    if (lane < NDIM) {
+      const double v = s_ext[lane];
+      e = v > 0.0 ? v : 0.0;
+    }
+    warp_argmax_first<kArgWidth>(e, idx);
+    max_dim = e > 0.0 ? idx : 0;
+  }
+  for (int e = lane; e < NDIM * PGN_NCODES; e += 32) {
+    const int d = e / PGN_NCODES;
+    const int c = e - d * PGN_NCODES;
+    const double inner = __fma_rn(s_tp[c], s_lo[d], __dmul_rn(s_tm[c], s_up[d]));
+    s_x[e] = __fma_rn(P.ranges[d], inner, P.lows[d]);
+  }
+  __syncwarp();
+}
+
+// ---- per-region epilogue: split axis, block reduction replay, null-rule error, stores ------------
+template <int NDIM>
+__device__ __forceinline__ void
+region_epilogue(const EvalParams& P, size_t reg, int lane, const double* s_f, const double* s_scale,
+                const double* s_norm, const double (&sa)[PGN_NRULES], const double (&sb)[PGN_NRULES],
+                double vol, int max_dim, double ratio, double one_minus_ratio)
+{
+  constexpr int kArgWidth = NDIM <= 16 ? 16 : 32;
+  const bool lo_half = lane < 16;
+  // split axis: first axis with the largest fourth difference (Sample.cuh:194-218)
+  int bisect;
+  {
+    double fd = 0.0;
+    int idx = lane;
+    if (lane < NDIM) {
+      const double f0 = s_f[0];
+      const double fp = s_f[1 + 2 * lane], fm = s_f[2 + 2 * lane];
+      const double gp = s_f[1 + 2 * lane + 2 * NDIM], gm = s_f[2 + 2 * lane + 2 * NDIM];
+      const double base = __dmul_rn(__dadd_rn(f0, f0), one_minus_ratio);
+      const double t = __fma_rn(ratio, __dadd_rn(fp, fm), base);
+      const double v = fabs(__dsub_rn(t, __dadd_rn(gp, gm)));
+      fd = v > 0.0 ? v : 0.0;
+    }
+    warp_argmax_first<kArgWidth>(fd, idx);
+    bisect = fd > 0.0 ? idx : max_dim;
+  }
+  // the reference's block reduction (Sample.cuh:49-83) replayed inside one warp
+  double tot[PGN_NRULES];
+#pragma unroll
+  for (int r = 0; r < PGN_NRULES; ++r) {
+    const double keep = lo_half ? sa[r] : sb[r];
+    const double send = lo_half ? sb[r] : sa[r];
+    const double recv = __shfl_xor_sync(0xffffffffu, send, 16);
+    double v = __dadd_rn(keep, recv);  // lanes 0-15: A[i]+A[i+16]; lanes 16-31: B[i]+B[i+16]
+    v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, 8, 16));
+    v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, 4, 16));
+    v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, 2, 16));
+    v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, 1, 16));
+    tot[r] = __dadd_rn(__shfl_sync(0xffffffffu, v, 0), __shfl_sync(0xffffffffu, v, 16));
+  }
+  // null-rule error (Sample.cuh:261-289): lane = 3*set + (rule-1)
+  double term = 0.0;
+  if (lane < 3 * PGN_NSETS) {
+    const int s = lane / 3;
+    const int k = lane - 3 * s;  // rule-1
+    const double a = k == 0 ? tot[1] : (k == 1 ? tot[2] : tot[3]);
+    const double b = k == 0 ? tot[2] : (k == 1 ? tot[3] : tot[4]);
+    term = __dmul_rn(fabs(__fma_rn(s_scale[s * PGN_NRULES + k + 1], a, b)),
+                     s_norm[s * PGN_NRULES + k + 1]);
+    term = fmax(0.0, term);
+  }
+  term = fmax(term, __shfl_down_sync(0xffffffffu, term, 12));
+  term = fmax(term, __shfl_down_sync(0xffffffffu, term, 6));
+  {
+    const double t3 = __shfl_down_sync(0xffffffffu, term, 3);
+    const double t6 = __shfl_down_sync(0xffffffffu, term, 6);
+    term = fmax(fmax(term, t3), t6);
+  }
+  const double e1 = __shfl_sync(0xffffffffu, term, 0);
+  const double e2 = __shfl_sync(0xffffffffu, term, 1);
+  const double e3 = __shfl_sync(0xffffffffu, term, 2);
+  if (lane == 0) {
+    const bool benign = (__dmul_rn(5.0, e1) <= e2) && (__dmul_rn(5.0, e2) <= e3);
+    const double inner = benign ? e1 : __dmul_rn(5.0, fmax(fmax(e1, e2), e3));
+    P.estimate[reg] = __dmul_rn(vol, tot[0]);
+    P.errorest[reg] = __dmul_rn(vol, inner);
+    P.axis[reg] = bisect;
+  }
+}
+
+// =================================================================================================
+// variant 1: shift/mask addressing from the 4-bit code words
+// =================================================================================================
+template <int NDIM>
+__host__ __device__ constexpr int
+per_warp_doubles()
+{
+  // coordinate table, first-chunk function values, lower, upper, extent
+  return NDIM * PGN_NCODES + 64 + 3 * NDIM;
+}
+
+template <int NDIM>
+__host__ __device__ constexpr size_t
+smem_bytes(bool codes_in_smem)
+{
+  return sizeof(double) * (PGN_NSETS * kWeightRow + 2 * PGN_NSETS * PGN_NRULES + 2 * PGN_NCODES +
+                           kWarpsPerBlock * per_warp_doubles<NDIM>()) +
+         (codes_in_smem ? sizeof(uint64_t) * static_cast<size_t>(feval_of(NDIM)) : 0);
+}
+
 template <typename F, int NDIM, bool BY_VALUE, bool CODES_IN_SMEM>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-evaluate_kernel(typename std::conditional<BY_VALUE, F, F*>::type fparam, const EvalParams P)
+evaluate_kernel(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const __grid_constant__ EvalParams P)
 {
   static_assert(NDIM >= 2 && NDIM <= PGN_MAX_NDIM, "4*ndim+1 must fit the 64 emulated threads");
-  constexpr int kArgWidth = NDIM <= 16 ? 16 : 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
 
   double* s_w = reinterpret_cast<double*>(smem_raw);         // [9][6]
@@ -155,55 +306,21 @@ evaluate_kernel(typename std::conditional<BY_VALUE, F, F*>::type fparam, const E
 
   // the functor: by value for empty/trivial ones, through a managed-memory copy otherwise
   // (reference: cuda_copy_to_managed / make_gpu_integrand, cudaMemoryUtil.h:181-196, 345-353)
-  F* fptr;
-  if constexpr (BY_VALUE)
-    fptr = &fparam;
-  else
-    fptr = fparam;
+  F* fptr = farg.get();
 
   const int feval = P.feval;
   const int full_chunks = feval >> 6;  // chunks of 64 points in which every emulated thread works
   const double jac = P.jacobian;
   const double ratio = P.ratio;
   const double one_minus_ratio = __dsub_rn(1.0, ratio);
-  const bool lo_half = lane < 16;
 
   const size_t n = P.n;
   const size_t stride = static_cast<size_t>(gridDim.x) * kWarpsPerBlock;
   for (size_t reg = static_cast<size_t>(blockIdx.x) * kWarpsPerBlock + warp; reg < n; reg += stride) {
     __syncwarp();
-    // ---- region bounds (INIT_REGION_POOL, Phases.cuh:323-349)
-    if (lane < NDIM) {
-      const double lo = P.left[static_cast<size_t>(lane) * n + reg];
-      const double up = __dadd_rn(lo, P.length[static_cast<size_t>(lane) * n + reg]);
-      s_lo[lane] = lo;
-      s_up[lane] = up;
-      s_ext[lane] = __dsub_rn(up, lo);
-    }
-    __syncwarp();
-    double vol = s_ext[0];
-#pragma unroll
-    for (int d = 1; d < NDIM; ++d)
-      vol = __dmul_rn(vol, s_ext[d]);
+    double vol;
     int max_dim;
-    {
-      double e = 0.0;
-      int idx = lane;
-      if (lane < NDIM) {
-        const double v = s_ext[lane];
-        e = v > 0.0 ? v : 0.0;
-      }
-      warp_argmax_first<kArgWidth>(e, idx);
-      max_dim = e > 0.0 ? idx : 0;
-    }
-    // ---- coordinate table: x(axis, code) with the reference's operation sequence
-    for (int e = lane; e < NDIM * PGN_NCODES; e += 32) {
-      const int d = e / PGN_NCODES;
-      const int c = e - d * PGN_NCODES;
-      const double inner = __fma_rn(s_tp[c], s_lo[d], __dmul_rn(s_tm[c], s_up[d]));
-      s_x[e] = __fma_rn(P.ranges[d], inner, P.lows[d]);
-    }
-    __syncwarp();
+    region_prologue<NDIM>(P, reg, lane, s_tp, s_tm, s_lo, s_up, s_ext, s_x, vol, max_dim);
 
     double sa[PGN_NRULES], sb[PGN_NRULES];
 #pragma unroll
@@ -231,19 +348,19 @@ evaluate_kernel(typename std::conditional<BY_VALUE, F, F*>::type fparam, const E
       sum[4] = __fma_rn(fun, w4, sum[4]);
     };
 
-    // ---- chunk 0 keeps its function values for the fourth differences (Sample.cuh:176-219)
+    // chunk 0 keeps its function values for the fourth differences (Sample.cuh:176-219)
     {
       eval_point(lane, sa, true, lane);
       if (lane + 32 < feval)
         eval_point(lane + 32, sb, true, lane + 32);
     }
-    // ---- full chunks: both emulated threads of every lane are busy
+    // full chunks: both emulated threads of every lane are busy
     for (int k = 1; k < full_chunks; ++k) {
       const int p = (k << 6) + lane;
       eval_point(p, sa, false, 0);
       eval_point(p + 32, sb, false, 0);
     }
-    // ---- ragged tail (Sample.cuh:238-252)
+    // ragged tail (Sample.cuh:238-252)
     if (full_chunks >= 1) {
       const int p = (full_chunks << 6) + lane;
       if (p < feval)
@@ -252,83 +369,216 @@ evaluate_kernel(typename std::conditional<BY_VALUE, F, F*>::type fparam, const E
         eval_point(p + 32, sb, false, 0);
     }
     __syncwarp();
-
-    // ---- split axis: first axis with the largest fourth difference (Sample.cuh:194-218)
-    int bisect;
-    {
-      double fd = 0.0;
-      int idx = lane;
-      if (lane < NDIM) {
-        const double f0 = s_f[0];
-        const double fp = s_f[1 + 2 * lane], fm = s_f[2 + 2 * lane];
-        const double gp = s_f[1 + 2 * lane + 2 * NDIM], gm = s_f[2 + 2 * lane + 2 * NDIM];
-        const double base = __dmul_rn(__dadd_rn(f0, f0), one_minus_ratio);
-        const double t = __fma_rn(ratio, __dadd_rn(fp, fm), base);
-        const double v = fabs(__dsub_rn(t, __dadd_rn(gp, gm)));
-        fd = v > 0.0 ? v : 0.0;
-      }
-      warp_argmax_first<kArgWidth>(fd, idx);
-      bisect = fd > 0.0 ? idx : max_dim;
-    }
-
-    // ---- the reference's block reduction (Sample.cuh:49-83) replayed inside one warp
-    double tot[PGN_NRULES];
-#pragma unroll
-    for (int r = 0; r < PGN_NRULES; ++r) {
-      const double keep = lo_half ? sa[r] : sb[r];
-      const double send = lo_half ? sb[r] : sa[r];
-      const double recv = __shfl_xor_sync(0xffffffffu, send, 16);
-      double v = __dadd_rn(keep, recv);  // lanes 0-15: A[i]+A[i+16]; lanes 16-31: B[i]+B[i+16]
-      v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, 8, 16));
-      v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, 4, 16));
-      v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, 2, 16));
-      v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, 1, 16));
-      tot[r] = __dadd_rn(__shfl_sync(0xffffffffu, v, 0), __shfl_sync(0xffffffffu, v, 16));
-    }
-
-    // ---- null-rule error (Sample.cuh:261-289): lane = 3*set + (rule-1)
-    double term = 0.0;
-    if (lane < 3 * PGN_NSETS) {
-      const int s = lane / 3;
-      const int k = lane - 3 * s;  // rule-1
-      const double a = k == 0 ? tot[1] : (k == 1 ? tot[2] : tot[3]);
-      const double b = k == 0 ? tot[2] : (k == 1 ? tot[3] : tot[4]);
-      term = __dmul_rn(fabs(__fma_rn(s_scale[s * PGN_NRULES + k + 1], a, b)),
-                       s_norm[s * PGN_NRULES + k + 1]);
-      term = fmax(0.0, term);
-    }
-    term = fmax(term, __shfl_down_sync(0xffffffffu, term, 12));
-    term = fmax(term, __shfl_down_sync(0xffffffffu, term, 6));
-    {
-      const double t3 = __shfl_down_sync(0xffffffffu, term, 3);
-      const double t6 = __shfl_down_sync(0xffffffffu, term, 6);
-      term = fmax(fmax(term, t3), t6);
-    }
-    const double e1 = __shfl_sync(0xffffffffu, term, 0);
-    const double e2 = __shfl_sync(0xffffffffu, term, 1);
-    const double e3 = __shfl_sync(0xffffffffu, term, 2);
-    if (lane == 0) {
-      const bool benign = (__dmul_rn(5.0, e1) <= e2) && (__dmul_rn(5.0, e2) <= e3);
-      const double inner = benign ? e1 : __dmul_rn(5.0, fmax(fmax(e1, e2), e3));
-      P.estimate[reg] = __dmul_rn(vol, tot[0]);
-      P.errorest[reg] = __dmul_rn(vol, inner);
-      P.axis[reg] = bisect;
-    }
+    region_epilogue<NDIM>(P, reg, lane, s_f, s_scale, s_norm, sa, sb, vol, max_dim, ratio,
+                          one_minus_ratio);
   }
 }
 
-template <typename F>
-struct pass_by_value
-  : std::integral_constant<bool, std::is_empty<F>::value && std::is_trivially_copyable<F>::value &&
-                                   std::is_default_constructible<F>::value> {};
+// =================================================================================================
+// variant 2: byte-permute addressing
+// =================================================================================================
+template <int NDIM>
+struct BpLayout {
+  static constexpr int kCodeWords = NDIM <= 7 ? 2 : 4;  // 32-bit words per point
+  static constexpr int kWeightBytes = 512;              // w01 @0, w23 @144, w4 @288 (16-byte stride)
+  static constexpr int kXBytes = ((NDIM * PGN_NCODES * 8 + 255) / 256) * 256;
+  static constexpr int kWarpBytes = ((kXBytes + (64 + 3 * NDIM) * 8 + 255) / 256) * 256;
+  static constexpr int kMiscDoubles = 2 * PGN_NSETS * PGN_NRULES + 2 * PGN_NCODES;
+  static constexpr int kCodesOffset = kWeightBytes + kWarpsPerBlock * kWarpBytes + kMiscDoubles * 8;
+  static constexpr size_t
+  bytes()
+  {
+    return 256 /* alignment slack */ + kCodesOffset + 16 +
+           static_cast<size_t>(feval_of(NDIM)) * kCodeWords * 4;
+  }
+};
 
-// One instantiation's launch logic (called through the pgn_eval_fn trampoline).
+template <int IMM>
+__device__ __forceinline__ double
+lds_f64(uint32_t addr)
+{
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(IMM) : "memory");
+  return v;
+}
+template <int IMM>
+__device__ __forceinline__ double2
+lds_v2f64(uint32_t addr)
+{
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+%3];"
+               : "=d"(v.x), "=d"(v.y)
+               : "r"(addr), "n"(IMM)
+               : "memory");
+  return v;
+}
+
+template <int NDIM, int D>
+struct BpGather {
+  // x[d] = table[d][code byte d], for d = D .. NDIM-1
+  template <typename Words>
+  __device__ __forceinline__ static void
+  run(const Words& w, uint32_t xbase, double (&x)[NDIM])
+  {
+    const uint32_t word = D < 4 ? w.x : (D < 8 ? w.y : (D < 12 ? w.z : w.w));
+    x[D] = lds_f64<D * PGN_NCODES * 8>(__byte_perm(word, xbase, 0x7650 | (D & 3)));
+    BpGather<NDIM, D + 1>::run(w, xbase, x);
+  }
+};
+template <int NDIM>
+struct BpGather<NDIM, NDIM> {
+  template <typename Words>
+  __device__ __forceinline__ static void
+  run(const Words&, uint32_t, double (&)[NDIM])
+  {}
+};
+
+struct Words4 {
+  uint32_t x, y, z, w;
+};
+
+template <typename F, int NDIM, bool BY_VALUE>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const __grid_constant__ EvalParams P)
+{
+  static_assert(NDIM >= 2 && NDIM <= 12, "byte-permute variant keeps its code table in shared memory");
+  using L = BpLayout<NDIM>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t raw_addr = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw));
+  const uint32_t pad = (256u - (raw_addr & 255u)) & 255u;
+  unsigned char* sm = smem_raw + pad;      // 256-byte aligned, still a shared-space pointer
+  const uint32_t sm_addr = raw_addr + pad;
+
+  double* s_wt = reinterpret_cast<double*>(sm);  // weights, three sub-tables of 16-byte rows
+  double* s_scale = reinterpret_cast<double*>(sm + L::kWeightBytes + kWarpsPerBlock * L::kWarpBytes);
+  double* s_norm = s_scale + PGN_NSETS * PGN_NRULES;
+  double* s_tp = s_norm + PGN_NSETS * PGN_NRULES;
+  double* s_tm = s_tp + PGN_NCODES;
+  uint32_t* s_codes = reinterpret_cast<uint32_t*>(sm + ((L::kCodesOffset + 15) / 16) * 16);
+
+  // stage the tables: weights re-laid-out, 4-bit codes widened to one pre-scaled byte per axis
+  for (int i = threadIdx.x; i < PGN_NSETS * PGN_NRULES; i += blockDim.x) {
+    const int s = i / PGN_NRULES, r = i - s * PGN_NRULES;
+    const double w = __ldg(&P.weights[i]);
+    const int off = r < 2 ? (s * 2 + r) : (r < 4 ? (18 + s * 2 + (r - 2)) : (36 + s * 2));
+    s_wt[off] = w;
+    s_scale[i] = __ldg(&P.scale[i]);
+    s_norm[i] = __ldg(&P.norm[i]);
+  }
+  if (threadIdx.x < PGN_NCODES) {
+    s_tp[threadIdx.x] = P.half_plus_g[threadIdx.x];
+    s_tm[threadIdx.x] = P.half_minus_g[threadIdx.x];
+  }
+  for (int i = threadIdx.x; i < P.feval; i += blockDim.x) {
+    const uint64_t c4 = __ldg(&P.point_code[i]);
+    uint32_t words[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d)
+      words[d >> 2] |= static_cast<uint32_t>(((c4 >> (4 * d)) & 0xF) * 8u) << (8 * (d & 3));
+    const uint32_t set_byte = static_cast<uint32_t>(c4 >> 60) * 16u;
+    words[L::kCodeWords - 1] |= set_byte << 24;
+#pragma unroll
+    for (int k = 0; k < L::kCodeWords; ++k)
+      s_codes[i * L::kCodeWords + k] = words[k];
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  unsigned char* warp_area = sm + L::kWeightBytes + warp * L::kWarpBytes;
+  const uint32_t xbase = sm_addr + L::kWeightBytes + warp * L::kWarpBytes;  // 256-aligned
+  const uint32_t wbase = sm_addr;                                            // 256-aligned
+  double* s_x = reinterpret_cast<double*>(warp_area);
+  double* s_f = reinterpret_cast<double*>(warp_area + L::kXBytes);
+  double* s_lo = s_f + 64;
+  double* s_up = s_lo + NDIM;
+  double* s_ext = s_up + NDIM;
+
+  F* fptr = farg.get();
+
+  const int feval = P.feval;
+  const int full_chunks = feval >> 6;
+  const double jac = P.jacobian;
+  const double ratio = P.ratio;
+  const double one_minus_ratio = __dsub_rn(1.0, ratio);
+
+  const size_t n = P.n;
+  const size_t stride = static_cast<size_t>(gridDim.x) * kWarpsPerBlock;
+  for (size_t reg = static_cast<size_t>(blockIdx.x) * kWarpsPerBlock + warp; reg < n; reg += stride) {
+    __syncwarp();
+    double vol;
+    int max_dim;
+    region_prologue<NDIM>(P, reg, lane, s_tp, s_tm, s_lo, s_up, s_ext, s_x, vol, max_dim);
+
+    double sa[PGN_NRULES], sb[PGN_NRULES];
+#pragma unroll
+    for (int r = 0; r < PGN_NRULES; ++r)
+      sa[r] = sb[r] = 0.0;
+
+    auto eval_point = [&](int p, double (&sum)[PGN_NRULES], bool keep_f, int slot) {
+      Words4 cw;
+      if constexpr (L::kCodeWords == 2) {
+        const uint2 v = *reinterpret_cast<const uint2*>(s_codes + 2 * p);
+        cw.x = v.x;
+        cw.y = v.y;
+        cw.z = cw.w = 0u;
+      } else {
+        const uint4 v = *reinterpret_cast<const uint4*>(s_codes + 4 * p);
+        cw.x = v.x;
+        cw.y = v.y;
+        cw.z = v.z;
+        cw.w = v.w;
+      }
+      double x[NDIM];
+      BpGather<NDIM, 0>::run(cw, xbase, x);
+      const double fv = apply<F, NDIM>(*fptr, x);
+      const double fun = __dmul_rn(fv, jac);
+      if (keep_f)
+        s_f[slot] = fun;
+      const uint32_t last = L::kCodeWords == 2 ? cw.y : cw.w;
+      const uint32_t waddr = __byte_perm(last, wbase, 0x7653);
+      const double2 w01 = lds_v2f64<0>(waddr);
+      const double2 w23 = lds_v2f64<144>(waddr);
+      const double w4 = lds_f64<288>(waddr);
+      sum[0] = __fma_rn(fun, w01.x, sum[0]);
+      sum[1] = __fma_rn(fun, w01.y, sum[1]);
+      sum[2] = __fma_rn(fun, w23.x, sum[2]);
+      sum[3] = __fma_rn(fun, w23.y, sum[3]);
+      sum[4] = __fma_rn(fun, w4, sum[4]);
+    };
+
+    {
+      eval_point(lane, sa, true, lane);
+      if (lane + 32 < feval)
+        eval_point(lane + 32, sb, true, lane + 32);
+    }
+    for (int k = 1; k < full_chunks; ++k) {
+      const int p = (k << 6) + lane;
+      eval_point(p, sa, false, 0);
+      eval_point(p + 32, sb, false, 0);
+    }
+    if (full_chunks >= 1) {
+      const int p = (full_chunks << 6) + lane;
+      if (p < feval)
+        eval_point(p, sa, false, 0);
+      if (p + 32 < feval)
+        eval_point(p + 32, sb, false, 0);
+    }
+    __syncwarp();
+    region_epilogue<NDIM>(P, reg, lane, s_f, s_scale, s_norm, sa, sb, vol, max_dim, ratio,
+                          one_minus_ratio);
+  }
+}
+
+// One instantiation's launch logic (called through the pgn_eval_fn trampoline).  `functor` is the
+// host object when the functor travels by value (nullptr: default-construct it, which is what the
+// pre-instantiated stateless integrands do) and the managed-memory copy otherwise.
 template <typename F, int NDIM>
 int
-launch_evaluate(F* device_functor, const pgn_region_view* v)
+launch_evaluate(F* functor, const pgn_region_view* v)
 {
   constexpr bool kByValue = pass_by_value<F>::value;
-  if (v == nullptr || v->rule.ndim != NDIM)
+  if (v == nullptr || v->rule.ndim != NDIM || v->rule.feval != feval_of(NDIM))
     return PGN_ERR_INVALID;
   if (v->n == 0)
     return PGN_OK;
@@ -354,39 +604,46 @@ launch_evaluate(F* device_functor, const pgn_region_view* v)
   P.jacobian = v->jacobian;
   P.ratio = v->rule.ratio;
   P.feval = v->rule.feval;
-
-  const bool codes_in_smem = smem_bytes<NDIM>(P.feval, true) <= 100 * 1024;
-  const size_t smem = smem_bytes<NDIM>(P.feval, codes_in_smem);
   cudaStream_t stream = static_cast<cudaStream_t>(v->stream);
 
-  auto launch = [&](auto kernel) -> int {
+  FunctorArg<F, kByValue> farg = [&]() {
+    if constexpr (kByValue) {
+      if constexpr (std::is_default_constructible<F>::value) {
+        if (functor == nullptr)
+          return FunctorArg<F, true>{F{}};
+      }
+      return FunctorArg<F, true>{*functor};
+    } else {
+      return FunctorArg<F, false>{functor};
+    }
+  }();
+
+  auto launch = [&](auto kernel, size_t smem) -> int {
     static int blocks_per_sm = 0;  // per instantiation (the lambda is instantiated per kernel)
-    static size_t configured_smem = 0;
-    if (smem > configured_smem) {
+    if (blocks_per_sm == 0) {
       if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(smem)) != cudaSuccess)
         return PGN_ERR_CUDA;
-      configured_smem = smem;
-      blocks_per_sm = 0;
-    }
-    if (blocks_per_sm == 0) {
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kWarpsPerBlock * 32,
                                                         smem) != cudaSuccess ||
-          blocks_per_sm < 1)
+          blocks_per_sm < 1) {
+        blocks_per_sm = 0;
         return PGN_ERR_CUDA;
+      }
     }
     const size_t want = (v->n + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const size_t cap = static_cast<size_t>(v->sm_count > 0 ? v->sm_count : 148) * blocks_per_sm;
     const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
-    if constexpr (kByValue)
-      kernel<<<grid, kWarpsPerBlock * 32, smem, stream>>>(F{}, P);
-    else
-      kernel<<<grid, kWarpsPerBlock * 32, smem, stream>>>(device_functor, P);
+    kernel<<<grid, kWarpsPerBlock * 32, smem, stream>>>(farg, P);
     return cudaGetLastError() == cudaSuccess ? PGN_OK : PGN_ERR_CUDA;
   };
-  if (codes_in_smem)
-    return launch(evaluate_kernel<F, NDIM, kByValue, true>);
-  return launch(evaluate_kernel<F, NDIM, kByValue, false>);
+
+  constexpr bool kCodesFit = smem_bytes<NDIM>(true) <= 100 * 1024;
+  if constexpr (NDIM <= 12) {
+    if (v->reserved != kVariantShift)
+      return launch(evaluate_kernel_bp<F, NDIM, kByValue>, BpLayout<NDIM>::bytes());
+  }
+  return launch(evaluate_kernel<F, NDIM, kByValue, kCodesFit>, smem_bytes<NDIM>(kCodesFit));
 }
 
 template <typename F, int NDIM>
@@ -406,7 +663,10 @@ class Evaluator {
 public:
   explicit Evaluator(const F& f)
   {
-    if constexpr (!detail::pass_by_value<F>::value) {
+    if constexpr (detail::pass_by_value<F>::value) {
+      copy_ = static_cast<F*>(::operator new(sizeof(F)));  // host copy, handed to the launch by value
+      new (copy_) F(f);
+    } else {
       void* mem = nullptr;
       if (cudaMallocManaged(&mem, sizeof(F)) != cudaSuccess)
         throw std::bad_alloc();
@@ -418,7 +678,12 @@ public:
   }
   ~Evaluator()
   {
-    if (copy_ != nullptr) {
+    if (copy_ == nullptr)
+      return;
+    if constexpr (detail::pass_by_value<F>::value) {
+      copy_->~F();
+      ::operator delete(copy_);
+    } else {
       cudaDeviceSynchronize();
       copy_->~F();
       cudaFree(copy_);

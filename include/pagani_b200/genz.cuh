@@ -204,5 +204,51 @@ struct Discontinuous {
 };
 
 }  // namespace genz
+
+// Tiny integrands the reference's unit tests use (exposed as "families" 0, 7, 8 of the C ABI).
+namespace testfn {
+
+// family 0: RegionSampling.cu:18-46 / Easy_Integrals.cu:14-21 -- a constant
+template <int N>
+struct Constant {
+  static constexpr int ndim = N;
+  template <class... T>
+  PGN_HD double
+  operator()(T...) const
+  {
+    return 15.37;
+  }
+};
+
+// family 7: do_integration_from_c.cu:11-17 -- x*y (generalised: product of all coordinates)
+template <int N>
+struct Product {
+  static constexpr int ndim = N;
+  template <class... T>
+  PGN_HD double
+  operator()(T... xs) const
+  {
+    const double x[N] = {xs...};
+    double p = x[0];
+#pragma unroll
+    for (int k = 1; k < N; ++k)
+      p = p * x[k];
+    return p;
+  }
+};
+
+// family 8: NanIntegral.cu:15-23
+template <int N>
+struct NotANumber {
+  static constexpr int ndim = N;
+  template <class... T>
+  PGN_HD double
+  operator()(T...) const
+  {
+    return NAN;
+  }
+};
+
+}  // namespace testfn
 }  // namespace pagani_b200
 #endif

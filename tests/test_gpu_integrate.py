@@ -1,0 +1,108 @@
+"""End-to-end behaviour of integrate() through the C ABI, mirroring the reference's end-to-end
+tests (Easy_Integrals.cu, NanIntegral.cu, accuracy_improves_with_epsrel.cu, pagani_loop_test.cu)."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("family,ndim,true_value", [
+    (0, 2, 15.37),
+    (2, 6, 1.286889807581113e13),
+    (3, 8, 2.2751965817917756076e-10),
+    (4, 5, 1.79132603674879e-06),
+    (5, 8, 2.425217625641885e-06),
+    (6, 6, 1.5477367885091207413e8),
+])
+def test_easy_integrals(pg, family, ndim, true_value):
+    # Easy_Integrals.cu:54-148: epsrel 1e-3, epsabs 1e-12, Approx(true).epsilon(1e-3)
+    with pg.Workspace(ndim) as ws:
+        r = ws.integrate(pg.Genz(family, ndim), 1e-3, 1e-12)
+    assert r.status == 0
+    assert r.estimate == pytest.approx(true_value, rel=1e-3)
+    assert r.errorest / abs(r.estimate) <= 1e-3 or r.errorest <= 1e-12
+    assert r.neval > 0 and r.nregions > 0
+
+
+def test_f1_8d_true_value(pg):
+    with pg.Workspace(8) as ws:
+        g = pg.Genz(1, 8)
+        r = ws.integrate(g, 1e-5, 1e-40)
+    assert abs(r.estimate - 3.439557952183252e-05) <= 5 * r.errorest
+
+
+def test_nan_integrand_propagates(pg):
+    # NanIntegral.cu:25-37
+    with pg.Workspace(2) as ws:
+        r = ws.integrate(pg.Genz(8, 2), 1e-3, 1e-12)
+    assert math.isnan(r.estimate)
+    assert r.status == 1
+
+
+def test_accuracy_improves_with_epsrel(pg):
+    # accuracy_improves_with_epsrel.cu:38-67 (on the 6-D corner peak here)
+    with pg.Workspace(6) as ws:
+        g = pg.Genz(3, 6)
+        prev, eps = 1.0, 1e-3
+        while eps > 1e-6:
+            r = ws.integrate(g, eps, 1e-40)
+            assert r.status == 0
+            assert r.errorest <= prev
+            prev, eps = r.errorest, eps / 2
+
+
+def test_workspace_reuse_is_deterministic(pg):
+    # pagani_loop_test.cu:17-32 (shortened): repeated calls on one Workspace, identical results
+    with pg.Workspace(5) as ws:
+        g = pg.Genz(4, 5)
+        first = ws.integrate(g, 1e-3, 1e-40)
+        for _ in range(25):
+            assert ws.integrate(g, 1e-3, 1e-40) == first
+
+
+def test_both_overloads_agree_and_count_iters_like_the_reference(pg):
+    # Workspace.cuh:250 increments iters before the convergence test, :488 after the split
+    with pg.Workspace(6) as ws:
+        g = pg.Genz(6, 6)
+        plain = ws.integrate(g, 1e-3, 1e-40)
+        ws.uniform_split(2)
+        sub = ws.integrate(g, 1e-3, 1e-40, subregions=True)
+    assert (sub.estimate, sub.errorest, sub.nregions, sub.status) == (plain.estimate, plain.errorest, plain.nregions, plain.status)
+    assert sub.iters == plain.iters + 1
+
+
+def test_relerr_classification_off_keeps_every_region(pg):
+    with pg.Workspace(5, max_iters=6, trace=True) as ws:
+        r = ws.integrate(pg.Genz(5, 5), 1e-9, 1e-40, relerr_classification=False)
+        tr = ws.trace()
+    assert [t["nregions"] for t in tr] == [32 * 2**k for k in range(6)]
+    assert r.status == 1 and r.nregions == 32 * 2**6
+
+
+def test_neval_accounting(pg):
+    with pg.Workspace(8, trace=True) as ws:
+        r = ws.integrate(pg.Genz(5, 8), 1e-3, 1e-40)
+        tr = ws.trace()
+    assert r.neval == sum(t["nregions_global"] for t in tr) * pg.feval(8)
+
+
+def test_native_memory_mode_runs_and_agrees_until_the_filter_engages(pg):
+    with pg.Workspace(8, trace=True) as a, pg.Workspace(8, mem_mode="native", trace=True) as b:
+        ra = a.integrate(pg.Genz(1, 8), 1e-3, 1e-40)
+        rb = b.integrate(pg.Genz(1, 8), 1e-3, 1e-40)
+        ta, tb = a.trace(), b.trace()
+    assert ra.status == 0 and rb.status == 0
+    k = next(i for i, t in enumerate(ta) if t["heuristic_ran"])
+    assert [t["nregions"] for t in ta[:k + 1]] == [t["nregions"] for t in tb[:k + 1]]
+    assert abs(ra.estimate - rb.estimate) <= ra.errorest + rb.errorest
+
+
+def test_ten_dimensional_integrands(pg):
+    with pg.Workspace(10) as ws:
+        for fam in (5, 6):
+            g = pg.Genz(fam, 10)
+            r = ws.integrate(g, 1e-3, 1e-40)
+            assert r.status == 0
+            assert abs(r.estimate - g.true_value) <= 3 * r.errorest

@@ -1,0 +1,108 @@
+"""The partitioned path on real kernels: several ranks (processes) drive the engine on this box's
+GPU(s); collectives go through the host back-end (gloo) so that a single-GPU box can run it, and
+through NCCL when the box has at least two GPUs.  Checks: the partitioned run follows the
+single-rank trajectory (region counts per iteration, final result), every rank returns the same
+global result, and the repartition actually moves regions."""
+import json
+import os
+import socket
+
+import pytest
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir, backend, family, ndim, epsrel, rebalance):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch
+
+    import gpuintegration_b200 as pg
+    from gpuintegration_b200 import parallel
+
+    ngpu = torch.cuda.device_count()
+    device = rank % ngpu
+    torch.cuda.set_device(device)
+    parallel.init_process_group(backend="gloo" if backend == "host" else "nccl")
+    ws = pg.Workspace(ndim, device=device, trace=True)
+    if backend == "host":
+        parallel.attach_host_collectives(ws)
+    else:
+        parallel.attach_nccl(ws)
+    ws.set_rebalance(*rebalance)
+    r = ws.integrate(pg.Genz(family, ndim), epsrel, 1e-40)
+    tr = ws.trace()
+    with open(os.path.join(out_dir, f"rank{rank}.json"), "w") as f:
+        json.dump({"estimate": r.estimate, "errorest": r.errorest, "nregions": r.nregions, "status": r.status,
+                   "iters": r.iters, "neval": r.neval,
+                   "n_global": [t["nregions_global"] for t in tr], "n_local": [t["nregions"] for t in tr],
+                   "nactive": [t["nactive"] for t in tr], "rebalanced": [t["rebalanced"] for t in tr]}, f)
+    ws.close()
+    import torch.distributed as dist
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run(tmp_path, world, backend, family, ndim, epsrel, rebalance=(1.10, 4096)):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path), backend, family, ndim, epsrel, rebalance),
+             nprocs=world, join=True)
+    return [json.load(open(tmp_path / f"rank{r}.json")) for r in range(world)]
+
+
+def _single(pg, family, ndim, epsrel):
+    with pg.Workspace(ndim, trace=True) as ws:
+        r = ws.integrate(pg.Genz(family, ndim), epsrel, 1e-40)
+        return r, ws.trace()
+
+
+@pytest.mark.parametrize("world,family,ndim,epsrel", [(2, 5, 8, 1e-3), (3, 6, 6, 1e-3), (2, 1, 8, 1e-3)])
+def test_partitioned_run_follows_single_rank_trajectory(pg, tmp_path, world, family, ndim, epsrel):
+    ranks = _run(tmp_path, world, "host", family, ndim, epsrel)
+    r1, t1 = _single(pg, family, ndim, epsrel)
+    for rk in ranks:
+        assert rk["n_global"] == [t["nregions_global"] for t in t1]
+        assert rk["nactive"] == [t["nactive"] for t in t1]
+        assert (rk["status"], rk["nregions"], rk["iters"], rk["neval"]) == (r1.status, r1.nregions, r1.iters, r1.neval)
+        assert abs(rk["estimate"] - r1.estimate) <= 1e-12 * max(abs(r1.estimate), r1.errorest)
+        assert rk["estimate"] == ranks[0]["estimate"] and rk["errorest"] == ranks[0]["errorest"]
+    # the local lists partition the global one at every iteration
+    for i in range(len(t1)):
+        assert sum(rk["n_local"][i] for rk in ranks) == t1[i]["nregions_global"]
+
+
+def test_rebalance_moves_regions_and_keeps_the_trajectory(pg, tmp_path):
+    # the discontinuous integrand finishes most of the cube early: one rank's slice dries up
+    ranks = _run(tmp_path, 2, "host", 6, 6, 1e-3, rebalance=(1.0, 2))
+    r1, t1 = _single(pg, 6, 6, 1e-3)
+    assert any(any(rk["rebalanced"]) for rk in ranks)
+    for rk in ranks:
+        assert rk["n_global"] == [t["nregions_global"] for t in t1]
+        assert (rk["status"], rk["nregions"]) == (r1.status, r1.nregions)
+    # after a rebalance the ranks' local counts differ by at most 2 (pairs of children)
+    for i, flag in enumerate(ranks[0]["rebalanced"][:-1]):
+        if flag:
+            a, b = ranks[0]["n_local"][i + 1], ranks[1]["n_local"][i + 1]
+            assert abs(a - b) <= 2
+
+
+def test_nccl_backend_when_two_gpus(pg, tmp_path):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (NCCL refuses two ranks on one device)")
+    ranks = _run(tmp_path, 2, "nccl", 5, 8, 1e-3, rebalance=(1.0, 2))
+    r1, t1 = _single(pg, 5, 8, 1e-3)
+    for rk in ranks:
+        assert rk["n_global"] == [t["nregions_global"] for t in t1]
+        assert (rk["status"], rk["nregions"]) == (r1.status, r1.nregions)
+        assert abs(rk["estimate"] - r1.estimate) <= 1e-12 * max(abs(r1.estimate), r1.errorest)
