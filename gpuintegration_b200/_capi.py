@@ -79,6 +79,7 @@ class pgn_rule_view(C.Structure):
         ("half_minus_g", C.c_double * PGN_NCODES),
         ("ratio", C.c_double),
         ("two_one_minus_ratio_unused", C.c_double),
+        ("weights_host", C.c_double * (PGN_NSETS * PGN_NRULES)),
     ]
 
 

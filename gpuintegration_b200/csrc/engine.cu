@@ -8,6 +8,7 @@
 #include <limits>
 
 #include "stages.cuh"
+#include "threshold_search.cuh"
 
 namespace pgn {
 
@@ -226,13 +227,15 @@ Engine::~Engine()
                       &length_[0], &length_[1], &est_,        &err_raw_,    &err_ref_,    &axis_,
                       &active_,    &par_est_[0], &par_est_[1], &par_err_[0], &par_err_[1], &par_axis_,
                       &partials_,  &tile_count_, &tile_offset_, &done_,      &stats_dev_,  &stats_glob_,
-                      &digest_dev_, &pack_send_, &pack_recv_};
+                      &digest_dev_, &pack_send_, &pack_recv_, &sorted_err_, &search_tab_, &search_io_};
   for (DeviceBuf* b : all)
     b->release();
   if (host_local_)
     cudaFreeHost(host_local_);
   if (host_global_)
     cudaFreeHost(host_global_);
+  if (host_search_)
+    cudaFreeHost(host_search_);
   for (cudaEvent_t& e : ev_)
     if (e)
       cudaEventDestroy(e);
@@ -295,6 +298,12 @@ Engine::init()
   PGN_CUDA(cudaMallocHost(&host_local_, sizeof(double) * kHostStats));
   PGN_CUDA(cudaMallocHost(&host_global_, sizeof(double) * kHostStats));
   rank_counts_.assign(1, 0);
+  // bucket tables: count, start(+1), cursor, bucket_sum, suffix_sum(+1), suffix_count(+1), outside
+  PGN_TRY(search_tab_.reserve(8 * (6 * static_cast<size_t>(kMaxBuckets) + 8)));
+  PGN_TRY(search_io_.reserve(sizeof(SearchIO) + 16));
+  PGN_CUDA(cudaMallocHost(&host_search_, sizeof(SearchIO) + 16));
+  if (const char* hs = std::getenv("PGN_HOST_SEARCH"))
+    device_search_ = std::atoi(hs) == 0;
   if (const char* ev = std::getenv("PGN_EVAL_VARIANT"))
     eval_variant_ = std::atoi(ev);
   ready_ = true;
@@ -318,6 +327,8 @@ Engine::rule_view(pgn_rule_view* out) const
   }
   out->ratio = rule_.ratio;
   out->two_one_minus_ratio_unused = 0.0;
+  for (int i = 0; i < kSets * kRules; ++i)
+    out->weights_host[i] = rule_.weights[i];
   return PGN_OK;
 }
 
@@ -1016,6 +1027,46 @@ Engine::compact_and_split(size_t m_local, size_t m_global, bool* rebalanced)
 }
 
 // ------------------------------------------------------------------------------------------------
+// bucket partition for the device-side threshold search (threshold_search.cuh)
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void
+k_outside_to_double(const unsigned long long* outside, double* out)
+{
+  *out = static_cast<double>(*outside);
+}
+}  // namespace
+
+int
+Engine::prepare_search(const BucketPlan& plan, BucketTables* T)
+{
+  unsigned long long* base = search_tab_.as<unsigned long long>();
+  const size_t nbm = kMaxBuckets;
+  T->count = base;
+  T->start = base + nbm;               // nbm + 1
+  T->cursor = base + 2 * nbm + 1;
+  T->bucket_sum = reinterpret_cast<double*>(base + 3 * nbm + 1);
+  T->suffix_sum = reinterpret_cast<double*>(base + 4 * nbm + 1);    // nbm + 1
+  T->suffix_count = base + 5 * nbm + 2;                              // nbm + 1
+  T->outside = base + 6 * nbm + 3;
+  PGN_TRY(sorted_err_.reserve(sizeof(double) * std::max<size_t>(n_, 1)));
+  T->sorted = sorted_err_.as<double>();
+  PGN_CUDA(cudaMemsetAsync(search_tab_.ptr, 0, 8 * (6 * nbm + 8), stream_));
+  const unsigned grid = static_cast<unsigned>(std::min<size_t>((n_ + kScatterChunk - 1) / kScatterChunk,
+                                                               static_cast<size_t>(sm_count_) * 2));
+  if (n_ > 0)
+    ++launches_, k_bucket_count<<<grid, kSearchBlock, 0, stream_>>>(err_cur_, n_, plan, *T);
+  ++launches_, k_bucket_offsets<<<1, kSearchBlock, 0, stream_>>>(plan, *T);
+  if (n_ > 0) {
+    ++launches_, k_bucket_scatter<<<grid, kSearchBlock, 0, stream_>>>(err_cur_, n_, plan, *T);
+    ++launches_, k_bucket_sums<<<plan.nb, 256, 0, stream_>>>(plan, *T);
+  }
+  ++launches_, k_bucket_suffix<<<1, kSearchBlock, 0, stream_>>>(plan, *T);
+  PGN_CUDA(cudaGetLastError());
+  return PGN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // heuristic (memory-pressure) classifier
 // ------------------------------------------------------------------------------------------------
 double
@@ -1071,6 +1122,7 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
   }
   const double min_err = -host_global_[kNegMinSlot];
   const double max_err = host_global_[kMaxSlot];
+  const bool multi = comm_ && comm_->nranks > 1;
 
   double range_lo = min_err, range_hi = max_err;
   double threshold = iter_err / static_cast<double>(n_global);
@@ -1081,9 +1133,71 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
   double active_err_sum = 0.;
   size_t increases = 0, decreases = 0;
 
+  // Device-side search: partition the errors into value buckets once, then either run the whole
+  // bisection in one kernel (single rank) or answer every probe from the tables (several ranks).
+  BucketPlan plan;
+  BucketTables tables;
+  bool fast = device_search_ && make_bucket_plan(min_err, max_err, &plan);
+  if (fast)
+    PGN_TRY(prepare_search(plan, &tables));
+  bool searched = false;
+  if (fast && !multi) {
+    SearchIO* h = static_cast<SearchIO*>(host_search_);
+    std::memset(h, 0, sizeof *h);
+    h->iter_errorest = iter_err;
+    h->finished_errorest = fin_err;
+    h->cum_errorest = cum_err;
+    h->target_error = target_error;
+    h->min_err = min_err;
+    h->max_err = max_err;
+    h->n_regions = static_cast<double>(n_global);
+    h->max_percent_error_budget = max_percent_error_budget_;
+    h->max_active_regions_percentage = max_active_regions_percentage_;
+    unsigned long long* h_outside =
+      reinterpret_cast<unsigned long long*>(static_cast<char*>(host_search_) + sizeof(SearchIO));
+    PGN_CUDA(cudaMemcpyAsync(search_io_.ptr, h, sizeof *h, cudaMemcpyHostToDevice, stream_));
+    ++launches_, k_search<<<1, kSearchBlock, 0, stream_>>>(plan, tables, search_io_.as<SearchIO>());
+    PGN_CUDA(cudaGetLastError());
+    PGN_CUDA(cudaMemcpyAsync(h, search_io_.ptr, sizeof *h, cudaMemcpyDeviceToHost, stream_));
+    PGN_CUDA(cudaMemcpyAsync(h_outside, tables.outside, sizeof *h_outside, cudaMemcpyDeviceToHost,
+                             stream_));
+    PGN_CUDA(cudaStreamSynchronize(stream_));
+    if (*h_outside == 0) {
+      searched = true;
+      threshold = h->threshold;
+      active_err_sum = h->active_err_sum;
+      finished_errorest = h->extra_finished_errorest;
+      num_active = static_cast<size_t>(h->num_active);
+      pass_mem = h->pass_mem != 0;
+      pass_budget = h->pass_budget != 0;
+      out->probes += h->probes;
+    } else {
+      fast = false;  // NaN / inf / negative errors: keep the reference's flag*err semantics exactly
+    }
+  }
+
+  bool first_probe = true;
   auto probe = [&]() -> int {
-    PGN_TRY(run_threshold(0, threshold));
-    PGN_TRY(sync_stats(false));
+    if (fast) {
+      ++launches_, k_query<<<1, kSearchBlock, 0, stream_>>>(threshold, plan, tables,
+                                                   stats_dev_.as<double>() + kNumActive,
+                                                   stats_dev_.as<double>() + kSumActErr);
+      PGN_CUDA(cudaGetLastError());
+      if (first_probe) {
+        // the number of values the buckets cannot represent travels in an otherwise unused slot
+        ++launches_, k_outside_to_double<<<1, 1, 0, stream_>>>(tables.outside,
+                                                      stats_dev_.as<double>() + kSumEst);
+        PGN_CUDA(cudaGetLastError());
+      }
+      PGN_TRY(sync_stats(false));
+      if (first_probe && host_global_[kSumEst] != 0.0)
+        fast = false;  // some rank saw NaN / inf: redo this probe with the full pass
+      first_probe = false;
+    }
+    if (!fast) {
+      PGN_TRY(run_threshold(0, threshold));
+      PGN_TRY(sync_stats(false));
+    }
     out->probes++;
     num_active = static_cast<size_t>(host_global_[kNumActive]);
     active_err_sum = host_global_[kSumActErr];
@@ -1093,47 +1207,49 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
     return PGN_OK;
   };
 
-  do {
-    if (!pass_mem && increases <= 20) {
-      pass_mem = false;
-      size_t attempts = 0;
-      while (!pass_mem && attempts < 20) {
-        PGN_TRY(probe());
-        if (!pass_mem) {
-          range_lo = threshold;
-          threshold += std::fabs(range_hi - threshold) * .5;
-        }
-        attempts++;
-      }
-      increases++;
-    }
-    if (pass_mem) {
-      const double extra = iter_err - active_err_sum - fin_err;
-      const double budget = target_error - cum_err;
-      pass_budget = extra <= max_percent_error_budget_ * budget;
-      finished_errorest = extra;
-      if (!pass_budget && decreases <= 20) {
-        range_hi = threshold;
-        threshold -= std::fabs(range_lo - threshold) * .5;
+  if (!searched) {
+    do {
+      if (!pass_mem && increases <= 20) {
         pass_mem = false;
-        decreases++;
+        size_t attempts = 0;
+        while (!pass_mem && attempts < 20) {
+          PGN_TRY(probe());
+          if (!pass_mem) {
+            range_lo = threshold;
+            threshold += std::fabs(range_hi - threshold) * .5;
+          }
+          attempts++;
+        }
+        increases++;
       }
-    }
-    const bool exhausted = decreases >= 20 || increases >= 20;
-    if (exhausted && max_percent_error_budget_ < .7) {
-      max_percent_error_budget_ += 0.1;
-      decreases = 0;
-      increases = 0;
-      range_lo = min_err;
-      range_hi = max_err;
-      threshold = iter_err / static_cast<double>(n_global);
-    } else if (exhausted && max_percent_error_budget_ >= .7 &&
-               max_active_regions_percentage_ <= .7) {
-      max_active_regions_percentage_ += .1;
-    } else if (exhausted) {
-      break;
-    }
-  } while (!pass_mem || !pass_budget);
+      if (pass_mem) {
+        const double extra = iter_err - active_err_sum - fin_err;
+        const double budget = target_error - cum_err;
+        pass_budget = extra <= max_percent_error_budget_ * budget;
+        finished_errorest = extra;
+        if (!pass_budget && decreases <= 20) {
+          range_hi = threshold;
+          threshold -= std::fabs(range_lo - threshold) * .5;
+          pass_mem = false;
+          decreases++;
+        }
+      }
+      const bool exhausted = decreases >= 20 || increases >= 20;
+      if (exhausted && max_percent_error_budget_ < .7) {
+        max_percent_error_budget_ += 0.1;
+        decreases = 0;
+        increases = 0;
+        range_lo = min_err;
+        range_hi = max_err;
+        threshold = iter_err / static_cast<double>(n_global);
+      } else if (exhausted && max_percent_error_budget_ >= .7 &&
+                 max_active_regions_percentage_ <= .7) {
+        max_active_regions_percentage_ += .1;
+      } else if (exhausted) {
+        break;
+      }
+    } while (!pass_mem || !pass_budget);
+  }
 
   max_active_regions_percentage_ = .5;
   max_percent_error_budget_ = .25;
@@ -1281,6 +1397,8 @@ Engine::integrate(pgn_eval_fn fn, void* user, const pgn_integrate_args& args, pg
     if (tracing)
       cudaEventRecord(ev_[2], stream_);
     PGN_TRY(heuristic_classify(n_global, iter_est, iter_err, fin_err, cum_err, &hs));
+    if (tracing)
+      cudaEventRecord(ev_[3], stream_);
     st.heuristic_ran = hs.ran;
     st.heuristic_probes = hs.probes;
     st.threshold = hs.threshold;
@@ -1300,8 +1418,13 @@ Engine::integrate(pgn_eval_fn fn, void* user, const pgn_integrate_args& args, pg
       st.cum_estimate = cum_est;
       st.cum_errorest = cum_err;
       st.nactive = m_global;
-      if (tracing)
+      if (tracing) {
+        cudaEventSynchronize(ev_[3]);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_[2], ev_[3]);
+        st.heuristic_ms = ms;
         trace_.push_back(st);
+      }
       done = true;
       break;
     }
@@ -1315,8 +1438,6 @@ Engine::integrate(pgn_eval_fn fn, void* user, const pgn_integrate_args& args, pg
 
     // filter + split
     nregions += n_global - m_global;
-    if (tracing)
-      cudaEventRecord(ev_[3], stream_);
     if (m_global == 0) {
       n_ = 0;
       n_global = 0;

@@ -117,6 +117,8 @@ private:
   };
   int heuristic_classify(size_t n_global, double iter_est, double iter_err, double fin_err,
                          double cum_err, HeuristicOutcome* out);
+  // bucket partition of the current errors for the device-side threshold search
+  int prepare_search(const struct BucketPlan& plan, struct BucketTables* tables);
   double mem_capacity_bytes() const;
 
   int ndim_;
@@ -154,6 +156,10 @@ private:
   std::vector<size_t> rank_counts_;  // active regions per rank after the last flag-changing stage
   // rebalance staging
   DeviceBuf pack_send_, pack_recv_;
+  // heuristic threshold search: errors grouped by value bucket, bucket tables, search in/out block
+  DeviceBuf sorted_err_, search_tab_, search_io_;
+  void* host_search_ = nullptr;  // pinned mirror of search_io_ (SearchIO + the `outside` counter)
+  bool device_search_ = true;    // env PGN_HOST_SEARCH=1 forces the probe-per-pass search
 
   ConvergenceTracker tracker_;
   double max_percent_error_budget_ = .25;

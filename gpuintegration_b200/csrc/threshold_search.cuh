@@ -1,0 +1,459 @@
+// Device-side threshold search of the heuristic (memory-pressure) classifier.
+//
+// Reference: Heuristic_classifier::classify (cuda/pagani/quad/GPUquad/heuristic_classifier.cuh:362-451)
+// bisects an error threshold on the HOST; every probe is a flag kernel over all regions
+// (device_set_true_for_larger_than, :60-72), a thrust::reduce (count) and a thrust::inner_product
+// (sum of the errors above the threshold), each with a synchronous copy back -- up to several hundred
+// probes per classification on a 16 M-region list.
+//
+// Here the error array is partitioned ONCE into value buckets (the bit pattern of a non-negative double
+// is monotone in its value, so a bucket is a range of leading bits), and a probe becomes
+//     count(err > t) = count of all higher buckets  +  a scan of the one bucket that contains t
+// which a single thread block answers in a few microseconds.  The whole bisection (the reference's exact
+// threshold sequence and decisions) then runs inside ONE kernel, k_search, with no host round trip;
+// multi-rank runs use the same per-probe query (k_query) and all-reduce its two numbers.
+//
+// Sums are order independent by construction: inside a bucket every element has the same exponent, so
+// the mantissas are added as integers (exactly), and bucket totals are combined in a fixed order.
+// That makes the probe results -- and therefore the region trajectory -- run-to-run deterministic even
+// though the scatter uses atomics.
+#ifndef PGN_THRESHOLD_SEARCH_CUH
+#define PGN_THRESHOLD_SEARCH_CUH
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+namespace pgn {
+
+constexpr int kSearchBlock = 1024;
+constexpr int kMaxBuckets = 2048;
+constexpr int kScatterPerThread = 8;
+constexpr int kScatterChunk = kSearchBlock * kScatterPerThread;
+
+struct BucketPlan {
+  int shift;     // key = bits >> shift
+  int mbits;     // mantissa bits in the key (52 - shift)
+  uint32_t klo;  // key of bucket 0; smaller keys are clamped into bucket 0
+  uint32_t nb;   // buckets in use (<= kMaxBuckets)
+};
+
+// Device tables of one partition (all sized for kMaxBuckets).
+struct BucketTables {
+  unsigned long long* count;    // [nb]      elements per bucket
+  unsigned long long* start;    // [nb + 1]  exclusive prefix of count
+  unsigned long long* cursor;   // [nb]      scatter cursors
+  double* bucket_sum;           // [nb]      exact sum of the bucket, rounded once
+  double* suffix_sum;           // [nb + 1]  sum of buckets b..nb-1, accumulated from the top down
+  unsigned long long* suffix_count;  // [nb + 1]
+  unsigned long long* outside;  // [1] elements that are not finite non-negative numbers <= max
+  double* sorted;               // [n] the errors grouped by bucket
+};
+
+__host__ __device__ inline uint32_t
+bucket_of(unsigned long long bits, const BucketPlan& p)
+{
+  const unsigned long long k = bits >> p.shift;  // shift >= 40: fits 24 bits
+  const uint32_t kk = static_cast<uint32_t>(k);
+  return kk < p.klo ? 0u : kk - p.klo;  // >= nb: not a finite non-negative value <= max
+}
+
+// Biased exponent (clamped to >= 1, i.e. subnormals use the scale of the smallest normal) of the
+// upper edge of bucket b: the common scale of the bucket's integer sum.
+__host__ __device__ inline int
+bucket_exponent(uint32_t b, const BucketPlan& p)
+{
+  const int e = static_cast<int>(((p.klo + b) >> p.mbits) & 0x7ffu);
+  return e < 1 ? 1 : e;
+}
+
+// value = mant * 2^(eref - 1075) (truncated when the element's own exponent is smaller, which only
+// happens in the clamped bucket 0)
+__device__ __forceinline__ unsigned long long
+scaled_mantissa(unsigned long long bits, int eref)
+{
+  const int e = static_cast<int>((bits >> 52) & 0x7ffu);
+  const unsigned long long m = bits & 0xfffffffffffffull;
+  const unsigned long long mant = e ? (m | (1ull << 52)) : m;
+  const int s = eref - (e < 1 ? 1 : e);
+  return s <= 0 ? mant : (s < 64 ? mant >> s : 0ull);
+}
+
+// sum = (hi * 2^32 + lo) * 2^(eref - 1075)
+__device__ __forceinline__ double
+integer_sum_to_double(unsigned long long lo, unsigned long long hi, int eref)
+{
+  const double v = __fma_rn(static_cast<double>(hi), 4294967296.0, static_cast<double>(lo));
+  return scalbn(v, eref - 1075);
+}
+
+// Host: choose the finest bucket width that covers [min_err, max_err] with <= kMaxBuckets buckets.
+inline bool
+make_bucket_plan(double min_err, double max_err, BucketPlan* p)
+{
+  if (!(min_err >= 0.0) || !(max_err >= min_err) || !std::isfinite(max_err))
+    return false;
+  unsigned long long lo, hi;
+  std::memcpy(&lo, &min_err, 8);
+  std::memcpy(&hi, &max_err, 8);
+  lo &= 0x7fffffffffffffffull;  // -0.0
+  for (int mb = 12; mb >= 0; --mb) {
+    const int shift = 52 - mb;
+    const unsigned long long span = (hi >> shift) - (lo >> shift) + 1;
+    if (span <= static_cast<unsigned long long>(kMaxBuckets)) {
+      p->shift = shift;
+      p->mbits = mb;
+      p->klo = static_cast<uint32_t>(lo >> shift);
+      p->nb = static_cast<uint32_t>(span);
+      return true;
+    }
+  }
+  // more than 2048 binades cannot happen (11 exponent bits); more than kMaxBuckets at mb = 0 can:
+  // keep the top kMaxBuckets binades and clamp everything smaller into bucket 0
+  p->shift = 52;
+  p->mbits = 0;
+  const uint32_t kmax = static_cast<uint32_t>(hi >> 52);
+  p->klo = kmax + 1 > static_cast<uint32_t>(kMaxBuckets) ? kmax + 1 - kMaxBuckets : 0u;
+  p->nb = kmax - p->klo + 1;
+  return true;
+}
+
+// ---- partition ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSearchBlock)
+k_bucket_count(const double* __restrict__ err, size_t n, BucketPlan plan, BucketTables T)
+{
+  __shared__ unsigned int s_hist[kMaxBuckets];
+  __shared__ unsigned int s_outside;
+  for (int k = threadIdx.x; k < kMaxBuckets; k += kSearchBlock)
+    s_hist[k] = 0u;
+  if (threadIdx.x == 0)
+    s_outside = 0u;
+  __syncthreads();
+  for (size_t i = static_cast<size_t>(blockIdx.x) * kSearchBlock + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * kSearchBlock) {
+    const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(err[i]));
+    const uint32_t b = bucket_of(bits, plan);
+    if (b < plan.nb)
+      atomicAdd(&s_hist[b], 1u);
+    else
+      atomicAdd(&s_outside, 1u);
+  }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < plan.nb; k += kSearchBlock) {
+    const unsigned int c = s_hist[k];
+    if (c)
+      atomicAdd(&T.count[k], static_cast<unsigned long long>(c));
+  }
+  if (threadIdx.x == 0 && s_outside)
+    atomicAdd(T.outside, static_cast<unsigned long long>(s_outside));
+}
+
+// one block: exclusive prefix of the bucket counts, cursors
+__global__ void __launch_bounds__(kSearchBlock)
+k_bucket_offsets(BucketPlan plan, BucketTables T)
+{
+  __shared__ unsigned long long s_scan[kSearchBlock];
+  // kMaxBuckets = 2 * kSearchBlock: two buckets per thread
+  const uint32_t b0 = 2u * threadIdx.x, b1 = b0 + 1u;
+  const unsigned long long c0 = b0 < plan.nb ? T.count[b0] : 0ull;
+  const unsigned long long c1 = b1 < plan.nb ? T.count[b1] : 0ull;
+  s_scan[threadIdx.x] = c0 + c1;
+  __syncthreads();
+  for (int off = 1; off < kSearchBlock; off <<= 1) {
+    const unsigned long long add = static_cast<int>(threadIdx.x) >= off ? s_scan[threadIdx.x - off] : 0ull;
+    __syncthreads();
+    s_scan[threadIdx.x] += add;
+    __syncthreads();
+  }
+  const unsigned long long before = s_scan[threadIdx.x] - (c0 + c1);
+  if (b0 < plan.nb) {
+    T.start[b0] = before;
+    T.cursor[b0] = before;
+  }
+  if (b1 < plan.nb) {
+    T.start[b1] = before + c0;
+    T.cursor[b1] = before + c0;
+  }
+  if (threadIdx.x == kSearchBlock - 1)
+    T.start[plan.nb] = s_scan[threadIdx.x];
+}
+
+// Scatter into bucket order.  A block handles chunks of 8192 elements: ranks inside the chunk come
+// from shared-memory atomics, one global atomic per (chunk, populated bucket) reserves the range.
+__global__ void __launch_bounds__(kSearchBlock)
+k_bucket_scatter(const double* __restrict__ err, size_t n, BucketPlan plan, BucketTables T)
+{
+  __shared__ unsigned int s_hist[kMaxBuckets];
+  __shared__ unsigned long long s_base[kMaxBuckets];
+  for (int k = threadIdx.x; k < kMaxBuckets; k += kSearchBlock)
+    s_hist[k] = 0u;
+  __syncthreads();
+  const size_t chunks = (n + kScatterChunk - 1) / kScatterChunk;
+  for (size_t c = blockIdx.x; c < chunks; c += gridDim.x) {
+    const size_t base = c * kScatterChunk;
+    double v[kScatterPerThread];
+    uint32_t b[kScatterPerThread];
+    unsigned int r[kScatterPerThread];
+#pragma unroll
+    for (int q = 0; q < kScatterPerThread; ++q) {
+      const size_t i = base + static_cast<size_t>(q) * kSearchBlock + threadIdx.x;
+      b[q] = 0xffffffffu;
+      if (i < n) {
+        v[q] = err[i];
+        const uint32_t bb = bucket_of(static_cast<unsigned long long>(__double_as_longlong(v[q])), plan);
+        if (bb < plan.nb) {
+          b[q] = bb;
+          r[q] = atomicAdd(&s_hist[bb], 1u);
+        }
+      }
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < plan.nb; k += kSearchBlock) {
+      const unsigned int cnt = s_hist[k];
+      if (cnt) {
+        s_base[k] = atomicAdd(&T.cursor[k], static_cast<unsigned long long>(cnt));
+        s_hist[k] = 0u;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kScatterPerThread; ++q)
+      if (b[q] != 0xffffffffu)
+        T.sorted[s_base[b[q]] + r[q]] = v[q];
+    __syncthreads();
+  }
+}
+
+// block-wide exact reduction of (count, lo, hi); result valid in every thread
+__device__ __forceinline__ void
+block_sum3(unsigned long long& a, unsigned long long& b, unsigned long long& c,
+           unsigned long long (*s_red)[3])
+{
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, off);
+    b += __shfl_xor_sync(0xffffffffu, b, off);
+    c += __shfl_xor_sync(0xffffffffu, c, off);
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();  // protect s_red from the previous use
+  if (lane == 0) {
+    s_red[w][0] = a;
+    s_red[w][1] = b;
+    s_red[w][2] = c;
+  }
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  a = lane < nw ? s_red[lane][0] : 0ull;
+  b = lane < nw ? s_red[lane][1] : 0ull;
+  c = lane < nw ? s_red[lane][2] : 0ull;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, off);
+    b += __shfl_xor_sync(0xffffffffu, b, off);
+    c += __shfl_xor_sync(0xffffffffu, c, off);
+  }
+}
+
+// one 256-thread block per bucket: exact sum of the bucket
+__global__ void __launch_bounds__(256)
+k_bucket_sums(BucketPlan plan, BucketTables T)
+{
+  __shared__ unsigned long long s_red[32][3];
+  for (uint32_t bk = blockIdx.x; bk < plan.nb; bk += gridDim.x) {
+    const unsigned long long lo_i = T.start[bk], hi_i = T.start[bk + 1];
+    const int eref = bucket_exponent(bk, plan);
+    unsigned long long cnt = 0, lo = 0, hi = 0;
+    for (unsigned long long i = lo_i + threadIdx.x; i < hi_i; i += blockDim.x) {
+      const unsigned long long m =
+        scaled_mantissa(static_cast<unsigned long long>(__double_as_longlong(T.sorted[i])), eref);
+      lo += m & 0xffffffffull;
+      hi += m >> 32;
+      ++cnt;
+    }
+    block_sum3(cnt, lo, hi, s_red);
+    if (threadIdx.x == 0)
+      T.bucket_sum[bk] = integer_sum_to_double(lo, hi, eref);
+  }
+}
+
+// one block: suffix sums / counts, accumulated from the top bucket down in a fixed order
+__global__ void __launch_bounds__(kSearchBlock)
+k_bucket_suffix(BucketPlan plan, BucketTables T)
+{
+  __shared__ double s_sum[kSearchBlock];
+  // thread t owns buckets nb-1-2t and nb-2-2t (descending): local sums, then an inclusive scan
+  const int nb = static_cast<int>(plan.nb);
+  const int k0 = nb - 1 - 2 * static_cast<int>(threadIdx.x), k1 = k0 - 1;
+  const double v0 = k0 >= 0 ? T.bucket_sum[k0] : 0.0;
+  const double v1 = k1 >= 0 ? T.bucket_sum[k1] : 0.0;
+  s_sum[threadIdx.x] = v0 + v1;
+  __syncthreads();
+  for (int off = 1; off < kSearchBlock; off <<= 1) {
+    const double add = static_cast<int>(threadIdx.x) >= off ? s_sum[threadIdx.x - off] : 0.0;
+    __syncthreads();
+    s_sum[threadIdx.x] += add;
+    __syncthreads();
+  }
+  const double before = threadIdx.x > 0 ? s_sum[threadIdx.x - 1] : 0.0;  // all buckets above k0
+  const unsigned long long total = T.start[nb];
+  if (k0 >= 0) {
+    T.suffix_sum[k0] = before + v0;
+    T.suffix_count[k0] = total - T.start[k0];
+  }
+  if (k1 >= 0) {
+    T.suffix_sum[k1] = (before + v0) + v1;
+    T.suffix_count[k1] = total - T.start[k1];
+  }
+  if (threadIdx.x == 0) {
+    T.suffix_sum[nb] = 0.0;
+    T.suffix_count[nb] = 0ull;
+  }
+}
+
+// ---- probe ----------------------------------------------------------------------------------------
+// count and sum of the errors strictly above t (block-collective, result in every thread)
+__device__ __forceinline__ void
+probe_above(double t, const BucketPlan& plan, const BucketTables& T, unsigned long long (*s_red)[3],
+            unsigned long long* count, double* sum)
+{
+  if (!(t == t)) {  // e > NaN is false for every e
+    *count = 0ull;
+    *sum = 0.0;
+    return;
+  }
+  if (t < 0.0) {
+    *count = T.suffix_count[0];
+    *sum = T.suffix_sum[0];
+    return;
+  }
+  const unsigned long long tb_bits = static_cast<unsigned long long>(__double_as_longlong(t)) & 0x7fffffffffffffffull;
+  const uint32_t tb = bucket_of(tb_bits, plan);
+  if (tb >= plan.nb) {  // t is above the largest error
+    *count = 0ull;
+    *sum = 0.0;
+    return;
+  }
+  const unsigned long long lo_i = T.start[tb], hi_i = T.start[tb + 1];
+  const int eref = bucket_exponent(tb, plan);
+  unsigned long long cnt = 0, lo = 0, hi = 0;
+  for (unsigned long long i = lo_i + threadIdx.x; i < hi_i; i += blockDim.x) {
+    const double e = T.sorted[i];
+    if (e > t) {
+      const unsigned long long m = scaled_mantissa(static_cast<unsigned long long>(__double_as_longlong(e)), eref);
+      lo += m & 0xffffffffull;
+      hi += m >> 32;
+      ++cnt;
+    }
+  }
+  block_sum3(cnt, lo, hi, s_red);
+  *count = T.suffix_count[tb + 1] + cnt;
+  *sum = T.suffix_sum[tb + 1] + integer_sum_to_double(lo, hi, eref);
+}
+
+// one probe for the host-driven (multi-rank) search: out[0] = count, out[1] = sum
+__global__ void __launch_bounds__(kSearchBlock)
+k_query(double t, BucketPlan plan, BucketTables T, double* out_count, double* out_sum)
+{
+  __shared__ unsigned long long s_red[32][3];
+  unsigned long long c;
+  double s;
+  probe_above(t, plan, T, s_red, &c, &s);
+  if (threadIdx.x == 0) {
+    *out_count = static_cast<double>(c);
+    *out_sum = s;
+  }
+}
+
+// Inputs / outputs of the whole search (single rank).
+struct SearchIO {
+  // in
+  double iter_errorest, finished_errorest, cum_errorest, target_error;
+  double min_err, max_err;
+  double n_regions;  // as a double (exact below 2^53)
+  double max_percent_error_budget, max_active_regions_percentage;
+  // out
+  double threshold, active_err_sum, extra_finished_errorest;
+  unsigned long long num_active;
+  int pass_mem, pass_budget, probes;
+};
+
+// Heuristic_classifier::classify (heuristic_classifier.cuh:362-451), statement for statement, with
+// every thread of the block running the same scalar control flow on the same values and the probe
+// (apply_threshold + reduction + inner_product, :283-325) answered from the bucket tables.
+__global__ void __launch_bounds__(kSearchBlock)
+k_search(BucketPlan plan, BucketTables T, SearchIO* io)
+{
+  __shared__ unsigned long long s_red[32][3];
+  const SearchIO in = *io;
+  const double n_d = in.n_regions;
+  double range_lo = in.min_err, range_hi = in.max_err;
+  double threshold = in.iter_errorest / n_d;
+  double max_budget = in.max_percent_error_budget;
+  double max_active = in.max_active_regions_percentage;
+  bool pass_mem = false, pass_budget = false;
+  unsigned long long num_active = 0;
+  double active_err_sum = 0.0, finished_errorest = 0.0;
+  unsigned int increases = 0, decreases = 0;
+  int probes = 0;
+
+  do {
+    if (!pass_mem && increases <= 20) {
+      pass_mem = false;
+      unsigned int attempts = 0;
+      while (!pass_mem && attempts < 20) {
+        probe_above(threshold, plan, T, s_red, &num_active, &active_err_sum);
+        ++probes;
+        const double pct = static_cast<double>(static_cast<int>(num_active)) /
+                           static_cast<double>(static_cast<int>(n_d));
+        pass_mem = pct <= max_active;
+        if (!pass_mem) {
+          range_lo = threshold;
+          threshold += fabs(range_hi - threshold) * .5;
+        }
+        attempts++;
+      }
+      increases++;
+    }
+    if (pass_mem) {
+      const double extra = in.iter_errorest - active_err_sum - in.finished_errorest;
+      const double budget = in.target_error - in.cum_errorest;
+      pass_budget = extra <= max_budget * budget;
+      finished_errorest = extra;
+      if (!pass_budget && decreases <= 20) {
+        range_hi = threshold;
+        threshold -= fabs(range_lo - threshold) * .5;
+        pass_mem = false;
+        decreases++;
+      }
+    }
+    const bool exhausted = decreases >= 20 || increases >= 20;
+    if (exhausted && max_budget < .7) {
+      max_budget += 0.1;
+      decreases = 0;
+      increases = 0;
+      range_lo = in.min_err;
+      range_hi = in.max_err;
+      threshold = in.iter_errorest / n_d;
+    } else if (exhausted && max_budget >= .7 && max_active <= .7) {
+      max_active += .1;
+    } else if (exhausted) {
+      break;
+    }
+  } while (!pass_mem || !pass_budget);
+
+  if (threadIdx.x == 0) {
+    io->threshold = threshold;
+    io->active_err_sum = active_err_sum;
+    io->extra_finished_errorest = finished_errorest;
+    io->num_active = num_active;
+    io->pass_mem = pass_mem ? 1 : 0;
+    io->pass_budget = pass_budget ? 1 : 0;
+    io->probes = probes;
+  }
+}
+
+}  // namespace pgn
+#endif

@@ -83,8 +83,10 @@ def attach_host_collectives(ws, group=None):
         rc = [rcount[r] for r in range(world)]
         ro = [roff[r] for r in range(world)]
         stot, rtot = sum(sc), sum(rc)
-        sbuf = torch.from_numpy(np.ctypeslib.as_array(send, shape=(max(stot, 1),)))
-        rbuf = torch.from_numpy(np.ctypeslib.as_array(recv, shape=(max(rtot, 1),)))
+        # a rank that sends (receives) nothing gets a NULL pointer from the engine
+        empty = torch.empty(0, dtype=torch.float64)
+        sbuf = torch.from_numpy(np.ctypeslib.as_array(send, shape=(stot,))) if stot else empty
+        rbuf = torch.from_numpy(np.ctypeslib.as_array(recv, shape=(rtot,))) if rtot else empty
         ops = []
         for peer in range(world):
             if peer == rank:

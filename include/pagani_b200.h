@@ -83,6 +83,7 @@ typedef struct pgn_rule_view {
   double half_minus_g[PGN_NCODES]; /* 0.5 - g(code) */
   double ratio;                 /* (g[set2]/g[set1])^2, Sample.cuh:195-196 */
   double two_one_minus_ratio_unused;
+  double weights_host[PGN_NSETS * PGN_NRULES]; /* host copy of `weights`: evaluators pass it in kernel parameters */
 } pgn_rule_view;
 
 /* What one evaluation launch sees: the SoA region store of this iteration and its outputs. */

@@ -45,6 +45,9 @@
 namespace pagani_b200 {
 
 constexpr int kWarpsPerBlock = 4;
+#ifndef PGN_EVAL_MIN_BLOCKS
+#define PGN_EVAL_MIN_BLOCKS 1
+#endif
 constexpr int kWeightRow = 6;  // 5 rule weights padded to 48 B so a row is three 16-byte loads
 
 // values of pgn_region_view::reserved
@@ -82,10 +85,43 @@ struct EvalParams {
   double ranges[PGN_MAX_NDIM + 1];
   double half_plus_g[PGN_NCODES];
   double half_minus_g[PGN_NCODES];
+  double wc[PGN_NSETS * PGN_NRULES];  // rule weights [set][rule] (byte-permute variant: constant bank)
+  uint8_t half_set[256];              // generator set of points 32j..32j+31 if they share one, else 0xFF
   double jacobian;
   double ratio;
   int feval;
 };
+
+// first point of generator set s (sets follow each other in point order, Rule.cuh:438-505)
+__host__ __device__ constexpr int
+set_begin(int n, int s)
+{
+  const int count[PGN_NSETS] = {1,
+                                2 * n,
+                                2 * n,
+                                2 * n,
+                                2 * n,
+                                2 * n * (n - 1),
+                                4 * n * (n - 1),
+                                4 * n * (n - 1) * (n - 2) / 3,
+                                1 << n};
+  int b = 0;
+  for (int k = 0; k < s; ++k)
+    b += count[k];
+  return b;
+}
+
+// generator set of point p: number of set boundaries at or below p
+template <int NDIM>
+__device__ __forceinline__ int
+set_of_point(int p)
+{
+  int s = 0;
+#pragma unroll
+  for (int k = 1; k < PGN_NSETS; ++k)
+    s += p >= set_begin(NDIM, k) ? 1 : 0;
+  return s;
+}
 
 // How the functor reaches the kernel: small trivially-copyable functors travel by value in the
 // kernel's constant parameter space (state reads cost nothing); anything else is read through a
@@ -379,17 +415,16 @@ evaluate_kernel(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const __gr
 // =================================================================================================
 template <int NDIM>
 struct BpLayout {
-  static constexpr int kCodeWords = NDIM <= 7 ? 2 : 4;  // 32-bit words per point
-  static constexpr int kWeightBytes = 512;              // w01 @0, w23 @144, w4 @288 (16-byte stride)
+  static constexpr int kCodeWords = NDIM <= 8 ? 2 : 4;  // 32-bit words per point, one byte per axis
   static constexpr int kXBytes = ((NDIM * PGN_NCODES * 8 + 255) / 256) * 256;
   static constexpr int kWarpBytes = ((kXBytes + (64 + 3 * NDIM) * 8 + 255) / 256) * 256;
   static constexpr int kMiscDoubles = 2 * PGN_NSETS * PGN_NRULES + 2 * PGN_NCODES;
-  static constexpr int kCodesOffset = kWeightBytes + kWarpsPerBlock * kWarpBytes + kMiscDoubles * 8;
+  static constexpr int kCodesOffset = kWarpsPerBlock * kWarpBytes + kMiscDoubles * 8;
   static constexpr size_t
   bytes()
   {
     return 256 /* alignment slack */ + kCodesOffset + 16 +
-           static_cast<size_t>(feval_of(NDIM)) * kCodeWords * 4;
+           static_cast<size_t>(feval_of(NDIM)) * kCodeWords * 4 + feval_of(NDIM);
   }
 };
 
@@ -399,17 +434,6 @@ lds_f64(uint32_t addr)
 {
   double v;
   asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(IMM) : "memory");
-  return v;
-}
-template <int IMM>
-__device__ __forceinline__ double2
-lds_v2f64(uint32_t addr)
-{
-  double2 v;
-  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+%3];"
-               : "=d"(v.x), "=d"(v.y)
-               : "r"(addr), "n"(IMM)
-               : "memory");
   return v;
 }
 
@@ -437,8 +461,16 @@ struct Words4 {
   uint32_t x, y, z, w;
 };
 
+// The point loop is bound by shared-memory wavefronts (a 64-bit LDS of a warp costs two, a 128-bit
+// one four, whatever the addresses), so everything that is not a genuinely per-lane gather stays
+// out of shared memory:
+//   * code word of a point: one byte per axis, 8 bytes up to 8-D (one LDS.64);
+//   * rule weights: 32 consecutive points almost always belong to ONE generator set, whose five
+//     weights are then read from the kernel's constant parameter bank with a warp-uniform index
+//     (no LSU traffic); only the few half-chunks that straddle a set boundary look the set up per
+//     lane.
 template <typename F, int NDIM, bool BY_VALUE>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, PGN_EVAL_MIN_BLOCKS)
 evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const __grid_constant__ EvalParams P)
 {
   static_assert(NDIM >= 2 && NDIM <= 12, "byte-permute variant keeps its code table in shared memory");
@@ -449,19 +481,15 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
   unsigned char* sm = smem_raw + pad;      // 256-byte aligned, still a shared-space pointer
   const uint32_t sm_addr = raw_addr + pad;
 
-  double* s_wt = reinterpret_cast<double*>(sm);  // weights, three sub-tables of 16-byte rows
-  double* s_scale = reinterpret_cast<double*>(sm + L::kWeightBytes + kWarpsPerBlock * L::kWarpBytes);
+  double* s_scale = reinterpret_cast<double*>(sm + kWarpsPerBlock * L::kWarpBytes);
   double* s_norm = s_scale + PGN_NSETS * PGN_NRULES;
   double* s_tp = s_norm + PGN_NSETS * PGN_NRULES;
   double* s_tm = s_tp + PGN_NCODES;
   uint32_t* s_codes = reinterpret_cast<uint32_t*>(sm + ((L::kCodesOffset + 15) / 16) * 16);
+  unsigned char* s_set = reinterpret_cast<unsigned char*>(s_codes + feval_of(NDIM) * L::kCodeWords);
 
-  // stage the tables: weights re-laid-out, 4-bit codes widened to one pre-scaled byte per axis
+  // stage the tables: 4-bit codes widened to one pre-scaled byte per axis
   for (int i = threadIdx.x; i < PGN_NSETS * PGN_NRULES; i += blockDim.x) {
-    const int s = i / PGN_NRULES, r = i - s * PGN_NRULES;
-    const double w = __ldg(&P.weights[i]);
-    const int off = r < 2 ? (s * 2 + r) : (r < 4 ? (18 + s * 2 + (r - 2)) : (36 + s * 2));
-    s_wt[off] = w;
     s_scale[i] = __ldg(&P.scale[i]);
     s_norm[i] = __ldg(&P.norm[i]);
   }
@@ -469,25 +497,24 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
     s_tp[threadIdx.x] = P.half_plus_g[threadIdx.x];
     s_tm[threadIdx.x] = P.half_minus_g[threadIdx.x];
   }
-  for (int i = threadIdx.x; i < P.feval; i += blockDim.x) {
+  constexpr int kFeval = feval_of(NDIM);
+  for (int i = threadIdx.x; i < kFeval; i += blockDim.x) {
     const uint64_t c4 = __ldg(&P.point_code[i]);
     uint32_t words[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int d = 0; d < NDIM; ++d)
       words[d >> 2] |= static_cast<uint32_t>(((c4 >> (4 * d)) & 0xF) * 8u) << (8 * (d & 3));
-    const uint32_t set_byte = static_cast<uint32_t>(c4 >> 60) * 16u;
-    words[L::kCodeWords - 1] |= set_byte << 24;
 #pragma unroll
     for (int k = 0; k < L::kCodeWords; ++k)
       s_codes[i * L::kCodeWords + k] = words[k];
+    s_set[i] = static_cast<unsigned char>(c4 >> 60);
   }
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  unsigned char* warp_area = sm + L::kWeightBytes + warp * L::kWarpBytes;
-  const uint32_t xbase = sm_addr + L::kWeightBytes + warp * L::kWarpBytes;  // 256-aligned
-  const uint32_t wbase = sm_addr;                                            // 256-aligned
+  unsigned char* warp_area = sm + warp * L::kWarpBytes;
+  const uint32_t xbase = sm_addr + warp * L::kWarpBytes;  // 256-aligned
   double* s_x = reinterpret_cast<double*>(warp_area);
   double* s_f = reinterpret_cast<double*>(warp_area + L::kXBytes);
   double* s_lo = s_f + 64;
@@ -496,8 +523,7 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
 
   F* fptr = farg.get();
 
-  const int feval = P.feval;
-  const int full_chunks = feval >> 6;
+  constexpr int kFullChunks = kFeval >> 6;
   const double jac = P.jacobian;
   const double ratio = P.ratio;
   const double one_minus_ratio = __dsub_rn(1.0, ratio);
@@ -515,7 +541,8 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
     for (int r = 0; r < PGN_NRULES; ++r)
       sa[r] = sb[r] = 0.0;
 
-    auto eval_point = [&](int p, double (&sum)[PGN_NRULES], bool keep_f, int slot) {
+    // q: first point of the 32-point half-chunk the lane's point p belongs to (warp uniform)
+    auto eval_point = [&](int q, int p, double (&sum)[PGN_NRULES], bool keep_f, int slot) {
       Words4 cw;
       if constexpr (L::kCodeWords == 2) {
         const uint2 v = *reinterpret_cast<const uint2*>(s_codes + 2 * p);
@@ -535,34 +562,39 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
       const double fun = __dmul_rn(fv, jac);
       if (keep_f)
         s_f[slot] = fun;
-      const uint32_t last = L::kCodeWords == 2 ? cw.y : cw.w;
-      const uint32_t waddr = __byte_perm(last, wbase, 0x7653);
-      const double2 w01 = lds_v2f64<0>(waddr);
-      const double2 w23 = lds_v2f64<144>(waddr);
-      const double w4 = lds_f64<288>(waddr);
-      sum[0] = __fma_rn(fun, w01.x, sum[0]);
-      sum[1] = __fma_rn(fun, w01.y, sum[1]);
-      sum[2] = __fma_rn(fun, w23.x, sum[2]);
-      sum[3] = __fma_rn(fun, w23.y, sum[3]);
-      sum[4] = __fma_rn(fun, w4, sum[4]);
+      // uniform branch: one set for the whole half-chunk -> uniform constant-bank reads
+      int set = P.half_set[q >> 5];
+      if (set == 0xFF)
+        set = s_set[p];
+      const double* w = P.wc + set * PGN_NRULES;
+      sum[0] = __fma_rn(fun, w[0], sum[0]);
+      sum[1] = __fma_rn(fun, w[1], sum[1]);
+      sum[2] = __fma_rn(fun, w[2], sum[2]);
+      sum[3] = __fma_rn(fun, w[3], sum[3]);
+      sum[4] = __fma_rn(fun, w[4], sum[4]);
     };
 
+    // chunk 0 keeps its function values for the fourth differences (Sample.cuh:176-219)
     {
-      eval_point(lane, sa, true, lane);
-      if (lane + 32 < feval)
-        eval_point(lane + 32, sb, true, lane + 32);
+      eval_point(0, lane, sa, true, lane);
+      if (lane + 32 < kFeval)
+        eval_point(32, lane + 32, sb, true, lane + 32);
     }
-    for (int k = 1; k < full_chunks; ++k) {
-      const int p = (k << 6) + lane;
-      eval_point(p, sa, false, 0);
-      eval_point(p + 32, sb, false, 0);
+    // full chunks: both emulated threads of every lane are busy
+#pragma unroll 1
+    for (int k = 1; k < kFullChunks; ++k) {
+      const int q = k << 6;
+      eval_point(q, q + lane, sa, false, 0);
+      eval_point(q + 32, q + 32 + lane, sb, false, 0);
     }
-    if (full_chunks >= 1) {
-      const int p = (full_chunks << 6) + lane;
-      if (p < feval)
-        eval_point(p, sa, false, 0);
-      if (p + 32 < feval)
-        eval_point(p + 32, sb, false, 0);
+    // ragged tail (Sample.cuh:238-252)
+    if (kFullChunks >= 1) {
+      constexpr int q = kFullChunks << 6;
+      const int p = q + lane;
+      if (p < kFeval)
+        eval_point(q, p, sa, false, 0);
+      if (p + 32 < kFeval)
+        eval_point(q + 32, p + 32, sb, false, 0);
     }
     __syncwarp();
     region_epilogue<NDIM>(P, reg, lane, s_f, s_scale, s_norm, sa, sb, vol, max_dim, ratio,
@@ -601,6 +633,24 @@ launch_evaluate(F* functor, const pgn_region_view* v)
     P.half_plus_g[c] = v->rule.half_plus_g[c];
     P.half_minus_g[c] = v->rule.half_minus_g[c];
   }
+  for (int i = 0; i < PGN_NSETS * PGN_NRULES; ++i)
+    P.wc[i] = v->rule.weights_host[i];
+  if constexpr (NDIM <= 12) {
+    constexpr int kFeval = feval_of(NDIM);
+    static_assert((kFeval + 31) / 32 <= 256, "half_set table too small");
+    auto host_set_of = [](int p) {
+      int st = 0;
+      for (int k = 1; k < PGN_NSETS; ++k)
+        st += p >= set_begin(NDIM, k) ? 1 : 0;
+      return st;
+    };
+    for (int j = 0; j < 256; ++j) {
+      const int first = 32 * j, last = first + 31 < kFeval - 1 ? first + 31 : kFeval - 1;
+      P.half_set[j] = (first < kFeval && host_set_of(first) == host_set_of(last))
+                        ? static_cast<uint8_t>(host_set_of(first))
+                        : static_cast<uint8_t>(0xFF);
+    }
+  }
   P.jacobian = v->jacobian;
   P.ratio = v->rule.ratio;
   P.feval = v->rule.feval;
@@ -635,7 +685,8 @@ launch_evaluate(F* functor, const pgn_region_view* v)
     const size_t cap = static_cast<size_t>(v->sm_count > 0 ? v->sm_count : 148) * blocks_per_sm;
     const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
     kernel<<<grid, kWarpsPerBlock * 32, smem, stream>>>(farg, P);
-    return cudaGetLastError() == cudaSuccess ? PGN_OK : PGN_ERR_CUDA;
+    // peek: the engine reads (and clears) the error to report its text
+    return cudaPeekAtLastError() == cudaSuccess ? PGN_OK : PGN_ERR_CUDA;
   };
 
   constexpr bool kCodesFit = smem_bytes<NDIM>(true) <= 100 * 1024;

@@ -25,6 +25,26 @@
 namespace pagani_b200 {
 namespace genz {
 
+// explicitly rounded product / fused multiply-add, immune to the compiler's contraction choices
+PGN_HD inline double
+mul_rn(double a, double b)
+{
+#ifdef __CUDA_ARCH__
+  return __dmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+PGN_HD inline double
+fma_rn(double a, double b, double c)
+{
+#ifdef __CUDA_ARCH__
+  return __fma_rn(a, b, c);
+#else
+  return std::fma(a, b, c);
+#endif
+}
+
 // F_1: cos(x0 + 2 x1 + 3 x2 + ...)
 template <int N>
 struct Oscillatory {
@@ -116,10 +136,13 @@ struct CZero {
     static_assert(sizeof...(T) == N, "arity");
     const double x[N] = {xs...};
     const double beta = .5;
-    double t1 = -10. * fabs(x[0] - beta);
+    // one expression in the reference: -10|x0-b| - 10|x1-b| - ... ; nvcc (12.9, sm_100a) rounds the
+    // SECOND product and fuses the first, then chains FMAs (checked against the reference's SASS)
+    double t1 = mul_rn(-10., fabs(x[1] - beta));
+    t1 = fma_rn(-10., fabs(x[0] - beta), t1);
 #pragma unroll
-    for (int k = 1; k < N; ++k)
-      t1 = t1 - 10. * fabs(x[k] - beta);
+    for (int k = 2; k < N; ++k)
+      t1 = fma_rn(-10., fabs(x[k] - beta), t1);
     return exp(t1);
   }
 };
@@ -187,17 +210,22 @@ struct Discontinuous {
       outside = outside || (x[k] > Spec::beta(k));
     if (outside)
       return 0.;
+    // The reference writes the exponent as ONE expression a*x + b*y + ... ; which of the first two
+    // products nvcc rounds and which it fuses into the FMA chain is the compiler's choice (12.9,
+    // sm_100a: the second product is rounded at 5..7-D, the first at 8-D -- read off the reference
+    // kernel's SASS and re-checked by tests/test_integrand_sass.py), so it is pinned explicitly.
     double s;
     if (Spec::descending) {
-      s = Spec::alpha(N - 1) * x[N - 1];
+      s = mul_rn(Spec::alpha(N - 1), x[N - 1]);
 #pragma unroll
       for (int k = N - 2; k >= 0; --k)
-        s = s + Spec::alpha(k) * x[k];
+        s = fma_rn(Spec::alpha(k), x[k], s);
     } else {
-      s = Spec::alpha(0) * x[0];
+      s = mul_rn(Spec::alpha(1), x[1]);
+      s = fma_rn(Spec::alpha(0), x[0], s);
 #pragma unroll
-      for (int k = 1; k < N; ++k)
-        s = s + Spec::alpha(k) * x[k];
+      for (int k = 2; k < N; ++k)
+        s = fma_rn(Spec::alpha(k), x[k], s);
     }
     return exp(s);
   }

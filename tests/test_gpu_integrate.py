@@ -38,7 +38,10 @@ def test_nan_integrand_propagates(pg):
     with pg.Workspace(2) as ws:
         r = ws.integrate(pg.Genz(8, 2), 1e-3, 1e-12)
     assert math.isnan(r.estimate)
-    assert r.status == 1
+    # In the reference every null-rule term is NaN and max(0., NaN) keeps 0 (Sample.cuh:264-279), so each
+    # region reports errorest 0; accuracy_reached then passes on `errorest <= epsabs`
+    # (PaganiUtils.cuh:387-394) at the first iteration: status 0, NaN estimate, 16 regions.
+    assert r.errorest == 0.0 and r.status == 0 and r.nregions == 16 and r.iters == 0
 
 
 def test_accuracy_improves_with_epsrel(pg):
@@ -104,5 +107,7 @@ def test_ten_dimensional_integrands(pg):
         for fam in (5, 6):
             g = pg.Genz(fam, 10)
             r = ws.integrate(g, 1e-3, 1e-40)
-            assert r.status == 0
+            # with the reference's 16e9-byte memory model F_5_10D runs out of "memory" before 1e-3
+            # (status 1, like the reference: tests/test_gpu_parity.py compares that trajectory bit for bit)
+            assert r.status in (0, 1) and r.nregions > 0
             assert abs(r.estimate - g.true_value) <= 3 * r.errorest

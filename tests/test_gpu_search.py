@@ -1,0 +1,43 @@
+"""Device-side threshold search of the heuristic classifier (csrc/threshold_search.cuh) against the
+probe-per-pass search that restates Heuristic_classifier::classify on the host
+(reference heuristic_classifier.cuh:362-451): same threshold sequence, same accepted threshold, same
+flags, same trajectory."""
+import os
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ["nregions_global", "nactive", "heuristic_ran", "heuristic_probes", "threshold", "budget_overflow",
+        "dig_left", "dig_length", "dig_estimate", "dig_errorest", "dig_active"]
+
+
+def run(pg, family, ndim, epsrel, host_search):
+    old = os.environ.get("PGN_HOST_SEARCH")
+    os.environ["PGN_HOST_SEARCH"] = "1" if host_search else "0"
+    try:
+        with pg.Workspace(ndim, trace_arrays=True) as ws:
+            res = ws.integrate(pg.Genz(family, ndim), epsrel, 1e-40)
+            tr = ws.trace()
+    finally:
+        if old is None:
+            del os.environ["PGN_HOST_SEARCH"]
+        else:
+            os.environ["PGN_HOST_SEARCH"] = old
+    return res, tr
+
+
+# F_1_8D 1e-4: heuristic accepts thresholds and the run converges; 1e-5: ends in a failed search (status 1);
+# F_2_6D 1e-7: BASELINE config 3 (heuristic filter active); F_6_8D: many exactly-zero errors (clamped bucket)
+@pytest.mark.parametrize("family,ndim,epsrel", [(1, 8, 1e-4), (1, 8, 1e-5), (2, 6, 1e-7), (6, 8, 1e-5), (5, 10, 1e-5)])
+def test_device_search_equals_host_search(pg, family, ndim, epsrel):
+    res_d, tr_d = run(pg, family, ndim, epsrel, host_search=False)
+    res_h, tr_h = run(pg, family, ndim, epsrel, host_search=True)
+    assert any(t["heuristic_ran"] for t in tr_h), "case does not exercise the heuristic classifier"
+    assert len(tr_d) == len(tr_h)
+    for d, h in zip(tr_d, tr_h):
+        for k in KEYS:
+            assert d[k] == h[k], (d["iteration"], k, d[k], h[k])
+    assert res_d.status == res_h.status and res_d.nregions == res_h.nregions and res_d.iters == res_h.iters
+    assert res_d.estimate == res_h.estimate
+    assert res_d.errorest == pytest.approx(res_h.errorest, rel=1e-12)
