@@ -24,6 +24,9 @@ import sys
 import threading
 import time
 
+# the contract is ONE JSON line on stdout: NCCL's own banner / debug lines go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -222,12 +222,13 @@ Engine::~Engine()
     cudaSetDevice(device_);
     cudaStreamSynchronize(stream_);
   }
+  release_peer_mailboxes();
   delete comm_;
   DeviceBuf* all[] = {&d_codes_,   &d_weights_, &d_scale_,    &d_norm_,     &left_[0],    &left_[1],
                       &length_[0], &length_[1], &est_,        &err_raw_,    &err_ref_,    &axis_,
                       &active_,    &par_est_[0], &par_est_[1], &par_err_[0], &par_err_[1], &par_axis_,
                       &partials_,  &tile_count_, &tile_offset_, &done_,      &stats_dev_,  &stats_glob_,
-                      &digest_dev_, &pack_send_, &pack_recv_, &sorted_err_, &search_tab_, &search_io_};
+                      &digest_dev_, &pack_send_, &pack_recv_, &sorted_err_, &search_tab_, &search_io_, &mailbox_};
   for (DeviceBuf* b : all)
     b->release();
   if (host_local_)
@@ -487,6 +488,8 @@ Engine::launch_evaluate(pgn_eval_fn fn, void* user)
     return PGN_OK;
   pgn_region_view v;
   std::memset(&v, 0, sizeof v);
+  v.abi_version = PGN_ABI_VERSION;
+  v.view_bytes = static_cast<uint32_t>(sizeof v);
   v.left = left_[cur_].as<double>();
   v.length = length_[cur_].as<double>();
   v.n = n_;
@@ -515,7 +518,12 @@ int
 Engine::sync_stats(bool need_minmax)
 {
   const bool multi = comm_ && comm_->nranks > 1;
-  if (multi) {
+  if (multi && stats_fused_) {
+    // the statistics kernel all-reduced its vector itself (sums and [-min, max]) over NVLink
+    PGN_CUDA(cudaMemcpyAsync(host_global_, stats_glob_.ptr, sizeof(double) * kStatsLen,
+                             cudaMemcpyDeviceToHost, stream_));
+    need_minmax = true;
+  } else if (multi) {
     PGN_CUDA(cudaMemcpyAsync(stats_glob_.ptr, stats_dev_.ptr, sizeof(double) * kStatsLen,
                              cudaMemcpyDeviceToDevice, stream_));
     PGN_TRY(comm_->allreduce(stats_glob_.as<double>(), kStatsLen, kOpSum, stream_));
@@ -536,6 +544,10 @@ Engine::sync_stats(bool need_minmax)
   else if (!need_minmax) {
     host_global_[kNegMinSlot] = std::numeric_limits<double>::quiet_NaN();
     host_global_[kMaxSlot] = std::numeric_limits<double>::quiet_NaN();
+  }
+  if (multi && stats_fused_ && std::isnan(host_global_[kNumActive])) {
+    set_last_error("fused statistics all-reduce: a peer did not answer within the spin limit");
+    return PGN_ERR_NCCL;
   }
   const int w = comm_ ? comm_->nranks : 1;
   rank_counts_.resize(w);
@@ -562,14 +574,52 @@ write_empty_stats(double* dev, cudaStream_t s)
 }
 }  // namespace
 
+void
+Engine::fill_peer_box(PeerBox* box, long long spin_limit) const
+{
+  std::memset(box, 0, sizeof *box);
+  box->nranks = comm_->nranks;
+  box->rank = comm_->rank;
+  box->spin_limit = spin_limit;
+  for (int q = 0; q < comm_->nranks; ++q)
+    box->base[q] = static_cast<char*>(q == comm_->rank ? mailbox_.ptr : peer_mapped_[q]);
+}
+
+// Scratch of one statistics kernel.  With peer mailboxes the kernel's last block all-reduces the
+// statistics itself; every rank launches the same sequence of statistics kernels, so the exchange
+// numbers agree.
+TileScratch
+Engine::make_scratch()
+{
+  TileScratch ts;
+  std::memset(&ts, 0, sizeof ts);
+  ts.partials = partials_.as<double>();
+  ts.tile_count = tile_count_.as<uint32_t>();
+  ts.tile_offset = tile_offset_.as<uint64_t>();
+  ts.done = done_.as<unsigned int>();
+  ts.stats = stats_dev_.as<double>();
+  ts.rank = comm_ ? comm_->rank : 0;
+  ts.nranks = comm_ ? comm_->nranks : 1;
+  ts.stats_glob = stats_glob_.as<double>();
+  stats_fused_ = false;
+  if (comm_ && comm_->nranks > 1 && peer_ready_) {
+    // a peer may still be inside a long evaluation kernel: allow about a minute of skew
+    fill_peer_box(&ts.box, 120000000000ll);
+    ts.seq = ++stats_seq_;
+    stats_fused_ = true;
+  }
+  return ts;
+}
+
 int
 Engine::run_classify(double epsrel, int relerr)
 {
-  TileScratch ts{partials_.as<double>(), tile_count_.as<uint32_t>(), tile_offset_.as<uint64_t>(),
-                 done_.as<unsigned int>(), stats_dev_.as<double>(), comm_ ? comm_->rank : 0,
-                 comm_ ? comm_->nranks : 1};
+  TileScratch ts = make_scratch();
   if (n_ == 0) {
-    PGN_TRY(write_empty_stats(stats_dev_.as<double>(), stream_));
+    if (stats_fused_)
+      ++launches_, k_publish_empty_stats<<<1, kBlock, 0, stream_>>>(ts);
+    else
+      PGN_TRY(write_empty_stats(stats_dev_.as<double>(), stream_));
     err_cur_ = err_raw_.as<double>();
   } else if (parents_n_ > 0) {
     ++launches_, k_classify<true><<<tiles_for(n_), kBlock, 0, stream_>>>(
@@ -590,11 +640,14 @@ Engine::run_classify(double epsrel, int relerr)
 int
 Engine::run_threshold(int mode, double threshold)
 {
-  TileScratch ts{partials_.as<double>(), tile_count_.as<uint32_t>(), tile_offset_.as<uint64_t>(),
-                 done_.as<unsigned int>(), stats_dev_.as<double>(), comm_ ? comm_->rank : 0,
-                 comm_ ? comm_->nranks : 1};
-  if (n_ == 0)
+  TileScratch ts = make_scratch();
+  if (n_ == 0) {
+    if (stats_fused_) {
+      ++launches_, k_publish_empty_stats<<<1, kBlock, 0, stream_>>>(ts);
+      return cudaGetLastError() == cudaSuccess ? PGN_OK : PGN_ERR_CUDA;
+    }
     return write_empty_stats(stats_dev_.as<double>(), stream_);
+  }
   const int tiles = tiles_for(n_);
   if (mode == 0)
     ++launches_, k_threshold<0><<<tiles, kBlock, 0, stream_>>>(est_.as<double>(), err_cur_, active_.as<uint8_t>(),
@@ -612,11 +665,14 @@ Engine::run_threshold(int mode, double threshold)
 int
 Engine::run_recount()
 {
-  TileScratch ts{partials_.as<double>(), tile_count_.as<uint32_t>(), tile_offset_.as<uint64_t>(),
-                 done_.as<unsigned int>(), stats_dev_.as<double>(), comm_ ? comm_->rank : 0,
-                 comm_ ? comm_->nranks : 1};
-  if (n_ == 0)
+  TileScratch ts = make_scratch();
+  if (n_ == 0) {
+    if (stats_fused_) {
+      ++launches_, k_publish_empty_stats<<<1, kBlock, 0, stream_>>>(ts);
+      return cudaGetLastError() == cudaSuccess ? PGN_OK : PGN_ERR_CUDA;
+    }
     return write_empty_stats(stats_dev_.as<double>(), stream_);
+  }
   ++launches_, k_recount<<<tiles_for(n_), kBlock, 0, stream_>>>(est_.as<double>(), err_cur_,
                                                    active_.as<uint8_t>(), n_, ts);
   PGN_CUDA(cudaGetLastError());
@@ -1110,7 +1166,7 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
   out->ran = true;
 
   // Heuristic_classifier::classify (heuristic_classifier.cuh:362-451)
-  if (comm_ && comm_->nranks > 1) {
+  if (comm_ && comm_->nranks > 1 && !stats_fused_) {
     // min/max of the errors over all ranks (the local ones are still in stats_dev_)
     PGN_CUDA(cudaMemcpyAsync(stats_glob_.as<double>() + kNegMinSlot,
                              stats_dev_.as<double>() + kNegMinSlot, sizeof(double) * 2,
@@ -1141,7 +1197,7 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
   if (fast)
     PGN_TRY(prepare_search(plan, &tables));
   bool searched = false;
-  if (fast && !multi) {
+  if (fast && (!multi || peer_ready_)) {
     SearchIO* h = static_cast<SearchIO*>(host_search_);
     std::memset(h, 0, sizeof *h);
     h->iter_errorest = iter_err;
@@ -1153,16 +1209,30 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
     h->n_regions = static_cast<double>(n_global);
     h->max_percent_error_budget = max_percent_error_budget_;
     h->max_active_regions_percentage = max_active_regions_percentage_;
+    h->seq_base = peer_seq_;
     unsigned long long* h_outside =
       reinterpret_cast<unsigned long long*>(static_cast<char*>(host_search_) + sizeof(SearchIO));
+    PeerBox box;
+    std::memset(&box, 0, sizeof box);
+    if (multi)
+      fill_peer_box(&box, 4000000000ll);  // ~2 s of SM clocks: the ranks run this kernel in lock step
     PGN_CUDA(cudaMemcpyAsync(search_io_.ptr, h, sizeof *h, cudaMemcpyHostToDevice, stream_));
-    ++launches_, k_search<<<1, kSearchBlock, 0, stream_>>>(plan, tables, search_io_.as<SearchIO>());
+    if (multi)
+      ++launches_, k_search<true><<<1, kSearchBlock, 0, stream_>>>(plan, tables, search_io_.as<SearchIO>(), box);
+    else
+      ++launches_, k_search<false><<<1, kSearchBlock, 0, stream_>>>(plan, tables, search_io_.as<SearchIO>(), box);
     PGN_CUDA(cudaGetLastError());
     PGN_CUDA(cudaMemcpyAsync(h, search_io_.ptr, sizeof *h, cudaMemcpyDeviceToHost, stream_));
     PGN_CUDA(cudaMemcpyAsync(h_outside, tables.outside, sizeof *h_outside, cudaMemcpyDeviceToHost,
                              stream_));
     PGN_CUDA(cudaStreamSynchronize(stream_));
-    if (*h_outside == 0) {
+    if (multi)
+      peer_seq_ = h->seq_base;
+    if (h->probes == -1) {
+      set_last_error("multi-GPU threshold search: a peer did not answer within the spin limit");
+      return PGN_ERR_NCCL;
+    }
+    if (h->probes >= 0 && (multi || *h_outside == 0)) {
       searched = true;
       threshold = h->threshold;
       active_err_sum = h->active_err_sum;
@@ -1183,6 +1253,7 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
                                                    stats_dev_.as<double>() + kNumActive,
                                                    stats_dev_.as<double>() + kSumActErr);
       PGN_CUDA(cudaGetLastError());
+      stats_fused_ = false;  // k_query is not a statistics kernel: its two numbers go through the communicator
       if (first_probe) {
         // the number of values the buckets cannot represent travels in an otherwise unused slot
         ++launches_, k_outside_to_double<<<1, 1, 0, stream_>>>(tables.outside,
@@ -1495,7 +1566,86 @@ Engine::comm_init_nccl(const uint8_t* id, int nranks, int rank)
     return PGN_ERR_NCCL;
   }
   rank_counts_.assign(nranks, 0);
+  if (nranks > 1 && !std::getenv("PGN_NO_PEER_SEARCH")) {
+    const int rc = setup_peer_mailboxes();
+    if (rc != PGN_OK)
+      return rc;
+  }
   return PGN_OK;
+}
+
+// Every rank allocates a mailbox, publishes its cudaIpc handle (the 64 bytes travel as 64 doubles
+// through one SUM all-reduce of a one-hot table) and maps the mailboxes of all peers.
+int
+Engine::setup_peer_mailboxes()
+{
+  release_peer_mailboxes();
+  const int w = comm_->nranks, me = comm_->rank;
+  PGN_TRY(mailbox_.reserve(kMailboxBytes));
+  PGN_CUDA(cudaMemset(mailbox_.ptr, 0, kMailboxBytes));
+  cudaIpcMemHandle_t mine;
+  PGN_CUDA(cudaIpcGetMemHandle(&mine, mailbox_.ptr));
+  constexpr int kH = static_cast<int>(sizeof(cudaIpcMemHandle_t));
+  std::vector<double> table(static_cast<size_t>(w) * kH, 0.0);
+  const unsigned char* bytes = reinterpret_cast<const unsigned char*>(&mine);
+  for (int i = 0; i < kH; ++i)
+    table[static_cast<size_t>(me) * kH + i] = static_cast<double>(bytes[i]);
+  DeviceBuf xchg;
+  PGN_TRY(xchg.reserve(sizeof(double) * table.size()));
+  PGN_CUDA(cudaMemcpyAsync(xchg.ptr, table.data(), sizeof(double) * table.size(), cudaMemcpyHostToDevice,
+                           stream_));
+  int rc = comm_->allreduce(xchg.as<double>(), static_cast<int>(table.size()), kOpSum, stream_);
+  if (rc == PGN_OK &&
+      (cudaMemcpyAsync(table.data(), xchg.ptr, sizeof(double) * table.size(), cudaMemcpyDeviceToHost,
+                       stream_) != cudaSuccess ||
+       cudaStreamSynchronize(stream_) != cudaSuccess))
+    rc = PGN_ERR_CUDA;
+  xchg.release();
+  PGN_TRY(rc);
+  peer_mapped_.assign(w, nullptr);
+  bool ok = true;
+  for (int q = 0; q < w && ok; ++q) {
+    if (q == me)
+      continue;
+    cudaIpcMemHandle_t h;
+    unsigned char* hb = reinterpret_cast<unsigned char*>(&h);
+    for (int i = 0; i < kH; ++i)
+      hb[i] = static_cast<unsigned char>(table[static_cast<size_t>(q) * kH + i]);
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = false;  // no peer access between these devices: the host-driven search is used instead
+    } else {
+      peer_mapped_[q] = p;
+    }
+  }
+  // every rank must agree on whether the in-kernel path is usable
+  double agree = ok ? 0.0 : 1.0;
+  DeviceBuf flag;
+  PGN_TRY(flag.reserve(sizeof(double)));
+  PGN_CUDA(cudaMemcpyAsync(flag.ptr, &agree, sizeof agree, cudaMemcpyHostToDevice, stream_));
+  rc = comm_->allreduce(flag.as<double>(), 1, kOpSum, stream_);
+  if (rc == PGN_OK && (cudaMemcpyAsync(&agree, flag.ptr, sizeof agree, cudaMemcpyDeviceToHost, stream_) !=
+                         cudaSuccess ||
+                       cudaStreamSynchronize(stream_) != cudaSuccess))
+    rc = PGN_ERR_CUDA;
+  flag.release();
+  PGN_TRY(rc);
+  peer_ready_ = agree == 0.0;
+  peer_seq_ = 0;
+  if (!peer_ready_)
+    release_peer_mailboxes();
+  return PGN_OK;
+}
+
+void
+Engine::release_peer_mailboxes()
+{
+  for (void* p : peer_mapped_)
+    if (p)
+      cudaIpcCloseMemHandle(p);
+  peer_mapped_.clear();
+  peer_ready_ = false;
 }
 
 int

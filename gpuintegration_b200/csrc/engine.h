@@ -160,6 +160,17 @@ private:
   DeviceBuf sorted_err_, search_tab_, search_io_;
   void* host_search_ = nullptr;  // pinned mirror of search_io_ (SearchIO + the `outside` counter)
   bool device_search_ = true;    // env PGN_HOST_SEARCH=1 forces the probe-per-pass search
+  // NVLink peer mailboxes for the in-kernel all-reduce of the multi-rank search (threshold_search.cuh)
+  int setup_peer_mailboxes();
+  void release_peer_mailboxes();
+  DeviceBuf mailbox_;
+  std::vector<void*> peer_mapped_;       // cudaIpcOpenMemHandle results (nullptr for the own rank)
+  bool peer_ready_ = false;
+  unsigned long long peer_seq_ = 0;      // probes exchanged so far (identical on every rank)
+  unsigned long long stats_seq_ = 0;     // fused statistics all-reduces so far
+  bool stats_fused_ = false;             // the last statistics kernel already produced the global vector
+  struct TileScratch make_scratch();
+  void fill_peer_box(struct PeerBox* box, long long spin_limit) const;
 
   ConvergenceTracker tracker_;
   double max_percent_error_budget_ = .25;

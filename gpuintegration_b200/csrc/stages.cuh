@@ -23,6 +23,8 @@
 
 #include <cstdint>
 
+#include "peer.cuh"
+
 namespace pgn {
 
 constexpr int kBlock = 256;
@@ -46,8 +48,13 @@ struct TileScratch {
   uint32_t* tile_count;   // [tiles]   active regions per tile
   uint64_t* tile_offset;  // [tiles]   exclusive prefix of tile_count
   unsigned int* done;     // arrival counter (self-resetting)
-  double* stats;          // [kStatsLen] final values, see below
+  double* stats;          // [kStatsLen] final values of this rank, see below
   int rank, nranks;       // for the one-hot per-rank active count
+  // several ranks with NVLink peer mailboxes: the last block also all-reduces `stats` into
+  // `stats_glob` inside the kernel (peer.cuh); box.nranks <= 1 disables it
+  double* stats_glob;
+  unsigned long long seq;
+  PeerBox box;
 };
 // layout of `stats`: [0,8) the Stat slots; [8] = -min(err), [9] = max(err) (so one MAX all-reduce
 // serves both); [16 + r] = active regions of rank r (zero except the own rank: a SUM all-reduce of
@@ -57,6 +64,7 @@ constexpr int kMaxSlot = 9;
 constexpr int kRankSlot = 16;
 constexpr int kMaxRanks = 16;
 constexpr int kStatsLen = kRankSlot + kMaxRanks;
+static_assert(kStatsLen == kStatsDoubles && kMaxRanks == kMaxPeers, "stats vector and mailbox slot must agree");
 
 __global__ void
 k_uniform_split(double* left, double* length, size_t n, int parts, int ndim, double edge)
@@ -196,6 +204,12 @@ finalize(const TileScratch& ts, unsigned int tiles, bool with_offsets, Acc* s_wa
       ts.tile_offset[b] = run;
       run += __ldcg(&ts.tile_count[b]);
     }
+  }
+  if (ts.box.nranks > 1) {
+    // fused collective: sums in rank order, [-min, max] by maximum, straight over NVLink
+    __shared__ int s_peer_ok;
+    __syncthreads();
+    peer_allreduce_stats(ts.box, ts.seq, ts.stats, ts.stats_glob, kNegMinSlot, kMaxSlot + 1, &s_peer_ok);
   }
 }
 
@@ -349,6 +363,24 @@ k_recount(const double* __restrict__ est, const double* __restrict__ err,
     ts.tile_count[blockIdx.x] = static_cast<uint32_t>(a.v[kNumActive]);
   }
   dev::finalize(ts, gridDim.x, true, s_warp, s_scan);
+}
+
+// A rank whose region list is empty still takes part in the fused all-reduce.
+__global__ void __launch_bounds__(kBlock)
+k_publish_empty_stats(TileScratch ts)
+{
+  __shared__ int s_peer_ok;
+  if (threadIdx.x < kStatsLen) {
+    double v = 0.0;
+    if (threadIdx.x == kMinErr)
+      v = __longlong_as_double(0x7ff0000000000000LL);
+    if (threadIdx.x == kMaxErr || threadIdx.x == kNegMinSlot || threadIdx.x == kMaxSlot)
+      v = __longlong_as_double(0xfff0000000000000LL);
+    ts.stats[threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (ts.box.nranks > 1)
+    peer_allreduce_stats(ts.box, ts.seq, ts.stats, ts.stats_glob, kNegMinSlot, kMaxSlot + 1, &s_peer_ok);
 }
 
 struct CompactArgs {

@@ -26,12 +26,15 @@
 #include <cstdint>
 #include <cstring>
 
+#include "peer.cuh"
+
 namespace pgn {
 
 constexpr int kSearchBlock = 1024;
 constexpr int kMaxBuckets = 2048;
 constexpr int kScatterPerThread = 8;
 constexpr int kScatterChunk = kSearchBlock * kScatterPerThread;
+constexpr int kProbeCache = 1024;  // memo table of probe results (power of two)
 
 struct BucketPlan {
   int shift;     // key = bits >> shift
@@ -367,26 +370,39 @@ k_query(double t, BucketPlan plan, BucketTables T, double* out_count, double* ou
   }
 }
 
-// Inputs / outputs of the whole search (single rank).
+// Inputs / outputs of the whole search.
 struct SearchIO {
   // in
   double iter_errorest, finished_errorest, cum_errorest, target_error;
   double min_err, max_err;
-  double n_regions;  // as a double (exact below 2^53)
+  double n_regions;  // global, as a double (exact below 2^53)
   double max_percent_error_budget, max_active_regions_percentage;
+  unsigned long long seq_base;  // probes exchanged so far on this mailbox (several ranks)
   // out
   double threshold, active_err_sum, extra_finished_errorest;
   unsigned long long num_active;
-  int pass_mem, pass_budget, probes;
+  int pass_mem, pass_budget;
+  int probes;   // -1: a peer did not answer; -2: some rank holds NaN / inf / negative errors
+  int probes_computed;  // probes that were not answered from the memo table
 };
 
 // Heuristic_classifier::classify (heuristic_classifier.cuh:362-451), statement for statement, with
 // every thread of the block running the same scalar control flow on the same values and the probe
 // (apply_threshold + reduction + inner_product, :283-325) answered from the bucket tables.
+// MULTI: the per-probe count and sum are all-reduced over the ranks inside the kernel.
+template <bool MULTI>
 __global__ void __launch_bounds__(kSearchBlock)
-k_search(BucketPlan plan, BucketTables T, SearchIO* io)
+k_search(BucketPlan plan, BucketTables T, SearchIO* io, PeerBox box)
 {
   __shared__ unsigned long long s_red[32][3];
+  __shared__ int s_ok;
+  __shared__ unsigned long long c_key[kProbeCache];
+  __shared__ unsigned long long c_cnt[kProbeCache];
+  __shared__ double c_sum[kProbeCache];
+  for (int i = threadIdx.x; i < kProbeCache; i += blockDim.x)
+    c_key[i] = ~0ull;  // a NaN pattern: never cached
+  __syncthreads();
+  int computed = 0;
   const SearchIO in = *io;
   const double n_d = in.n_regions;
   double range_lo = in.min_err, range_hi = in.max_err;
@@ -398,14 +414,48 @@ k_search(BucketPlan plan, BucketTables T, SearchIO* io)
   double active_err_sum = 0.0, finished_errorest = 0.0;
   unsigned int increases = 0, decreases = 0;
   int probes = 0;
+  unsigned long long seq = in.seq_base;
+  const double outside_local = static_cast<double>(*T.outside);
 
   do {
     if (!pass_mem && increases <= 20) {
       pass_mem = false;
       unsigned int attempts = 0;
       while (!pass_mem && attempts < 20) {
-        probe_above(threshold, plan, T, s_red, &num_active, &active_err_sum);
+        // The reference restarts its bisection from the same threshold every time it relaxes a budget,
+        // so most probes of a long search repeat earlier ones: (global) results are memoised by the
+        // bit pattern of the threshold.  Every rank holds the same cache, so a hit needs no exchange.
+        const unsigned long long tbits = static_cast<unsigned long long>(__double_as_longlong(threshold));
+        const unsigned int slot =
+          static_cast<unsigned int>((tbits ^ (tbits >> 19) ^ (tbits >> 41)) & (kProbeCache - 1));
         ++probes;
+        if (c_key[slot] == tbits) {
+          num_active = c_cnt[slot];
+          active_err_sum = c_sum[slot];
+        } else {
+          probe_above(threshold, plan, T, s_red, &num_active, &active_err_sum);
+          if (MULTI) {
+            double cnt = static_cast<double>(num_active), sum = active_err_sum, outside = outside_local;
+            const bool ok = peer_allreduce3(box, ++seq, cnt, sum, outside, &s_ok);
+            if (!ok || outside != 0.0) {
+              if (threadIdx.x == 0) {
+                io->probes = ok ? -2 : -1;
+                io->seq_base = seq;
+              }
+              return;
+            }
+            num_active = static_cast<unsigned long long>(cnt);
+            active_err_sum = sum;
+          }
+          __syncthreads();  // every thread has read the old entry
+          if (threadIdx.x == 0 && threshold == threshold) {
+            c_key[slot] = tbits;
+            c_cnt[slot] = num_active;
+            c_sum[slot] = active_err_sum;
+          }
+          __syncthreads();
+          ++computed;
+        }
         const double pct = static_cast<double>(static_cast<int>(num_active)) /
                            static_cast<double>(static_cast<int>(n_d));
         pass_mem = pct <= max_active;
@@ -452,6 +502,8 @@ k_search(BucketPlan plan, BucketTables T, SearchIO* io)
     io->pass_mem = pass_mem ? 1 : 0;
     io->pass_budget = pass_budget ? 1 : 0;
     io->probes = probes;
+    io->probes_computed = computed;
+    io->seq_base = seq;
   }
 }
 

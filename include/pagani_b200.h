@@ -87,7 +87,10 @@ typedef struct pgn_rule_view {
 } pgn_rule_view;
 
 /* What one evaluation launch sees: the SoA region store of this iteration and its outputs. */
+#define PGN_ABI_VERSION 2u
 typedef struct pgn_region_view {
+  uint32_t abi_version; /* PGN_ABI_VERSION of the library that filled the view */
+  uint32_t view_bytes;  /* sizeof(pgn_region_view) there: an evaluator compiled against other headers refuses */
   const double* left;   /* [ndim][n]  lower corner in unit-cube coordinates (Sub_regions::dLeftCoord) */
   const double* length; /* [ndim][n]  edge lengths                       (Sub_regions::dLength)    */
   size_t n;             /* regions in this launch */

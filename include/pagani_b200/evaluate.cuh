@@ -44,10 +44,22 @@
 
 namespace pagani_b200 {
 
-constexpr int kWarpsPerBlock = 4;
-#ifndef PGN_EVAL_MIN_BLOCKS
-#define PGN_EVAL_MIN_BLOCKS 1
+#ifndef PGN_EVAL_WARPS
+#define PGN_EVAL_WARPS 4
 #endif
+constexpr int kWarpsPerBlock = PGN_EVAL_WARPS;
+#ifndef PGN_EVAL_MIN_BLOCKS
+#define PGN_EVAL_MIN_BLOCKS 4
+#endif
+
+// Launch-bound tuning knob of the evaluation kernel: resident 128-thread blocks per SM the register
+// allocation must allow (4 -> up to 128 registers per thread, 7 -> 72, 8 -> 64).  Cheap integrands
+// want registers (the point loop is latency bound), pow()-heavy ones want warps.  Specialise for a
+// functor type to override the default; the sweep behind the Genz values is in profiles/.
+template <typename F>
+struct EvalTuning {
+  static constexpr int kMinBlocks = PGN_EVAL_MIN_BLOCKS;
+};
 constexpr int kWeightRow = 6;  // 5 rule weights padded to 48 B so a row is three 16-byte loads
 
 // values of pgn_region_view::reserved
@@ -87,6 +99,7 @@ struct EvalParams {
   double half_minus_g[PGN_NCODES];
   double wc[PGN_NSETS * PGN_NRULES];  // rule weights [set][rule] (byte-permute variant: constant bank)
   uint8_t half_set[256];              // generator set of points 32j..32j+31 if they share one, else 0xFF
+  uint8_t chunk_set[128];             // the same for points 64k..64k+63
   double jacobian;
   double ratio;
   int feval;
@@ -470,7 +483,7 @@ struct Words4 {
 //     (no LSU traffic); only the few half-chunks that straddle a set boundary look the set up per
 //     lane.
 template <typename F, int NDIM, bool BY_VALUE>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, PGN_EVAL_MIN_BLOCKS)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, EvalTuning<F>::kMinBlocks)
 evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const __grid_constant__ EvalParams P)
 {
   static_assert(NDIM >= 2 && NDIM <= 12, "byte-permute variant keeps its code table in shared memory");
@@ -541,8 +554,8 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
     for (int r = 0; r < PGN_NRULES; ++r)
       sa[r] = sb[r] = 0.0;
 
-    // q: first point of the 32-point half-chunk the lane's point p belongs to (warp uniform)
-    auto eval_point = [&](int q, int p, double (&sum)[PGN_NRULES], bool keep_f, int slot) {
+    // f(x_p) * Jacobian of the lane's point p
+    auto point_value = [&](int p) -> double {
       Words4 cw;
       if constexpr (L::kCodeWords == 2) {
         const uint2 v = *reinterpret_cast<const uint2*>(s_codes + 2 * p);
@@ -559,19 +572,31 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
       double x[NDIM];
       BpGather<NDIM, 0>::run(cw, xbase, x);
       const double fv = apply<F, NDIM>(*fptr, x);
-      const double fun = __dmul_rn(fv, jac);
-      if (keep_f)
-        s_f[slot] = fun;
-      // uniform branch: one set for the whole half-chunk -> uniform constant-bank reads
-      int set = P.half_set[q >> 5];
-      if (set == 0xFF)
-        set = s_set[p];
-      const double* w = P.wc + set * PGN_NRULES;
+      return __dmul_rn(fv, jac);
+    };
+    auto accumulate = [&](double (&sum)[PGN_NRULES], double fun, const double* w) {
       sum[0] = __fma_rn(fun, w[0], sum[0]);
       sum[1] = __fma_rn(fun, w[1], sum[1]);
       sum[2] = __fma_rn(fun, w[2], sum[2]);
       sum[3] = __fma_rn(fun, w[3], sum[3]);
       sum[4] = __fma_rn(fun, w[4], sum[4]);
+    };
+    // generic path: q = first point of the 32-point half-chunk of p (warp uniform); the set is
+    // uniform for most half-chunks, otherwise looked up per lane
+    auto eval_point = [&](int q, int p, double (&sum)[PGN_NRULES], bool keep_f, int slot) {
+      const double fun = point_value(p);
+      if (keep_f)
+        s_f[slot] = fun;
+      int set = P.half_set[q >> 5];
+      if (set == 0xFF)
+        set = s_set[p];
+#ifdef PGN_DEBUG_UNIT_WEIGHTS  // timing experiment only (results are wrong): no weight fetch at all
+      const double w[5] = {1.0, 2.0, 3.0, 4.0, 5.0};
+      (void)set;
+#else
+      const double* w = P.wc + set * PGN_NRULES;
+#endif
+      accumulate(sum, fun, w);
     };
 
     // chunk 0 keeps its function values for the fourth differences (Sample.cuh:176-219)
@@ -580,12 +605,33 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
       if (lane + 32 < kFeval)
         eval_point(32, lane + 32, sb, true, lane + 32);
     }
-    // full chunks: both emulated threads of every lane are busy
+    // full chunks: both emulated threads of every lane are busy.  Runs of chunks whose 64 points all
+    // belong to one generator set (most of them) keep the five weights in (uniform) registers.
+    {
+      int k = 1;
 #pragma unroll 1
-    for (int k = 1; k < kFullChunks; ++k) {
-      const int q = k << 6;
-      eval_point(q, q + lane, sa, false, 0);
-      eval_point(q + 32, q + 32 + lane, sb, false, 0);
+      while (k < kFullChunks) {
+        const int st = P.chunk_set[k];
+        if (st != 0xFF) {
+          const double w[PGN_NRULES] = {P.wc[st * PGN_NRULES + 0], P.wc[st * PGN_NRULES + 1],
+                                        P.wc[st * PGN_NRULES + 2], P.wc[st * PGN_NRULES + 3],
+                                        P.wc[st * PGN_NRULES + 4]};
+#pragma unroll 1
+          do {
+            const int q = k << 6;
+            const double fa = point_value(q + lane);
+            const double fb = point_value(q + 32 + lane);
+            accumulate(sa, fa, w);
+            accumulate(sb, fb, w);
+            ++k;
+          } while (k < kFullChunks && P.chunk_set[k] == st);
+        } else {
+          const int q = k << 6;
+          eval_point(q, q + lane, sa, false, 0);
+          eval_point(q + 32, q + 32 + lane, sb, false, 0);
+          ++k;
+        }
+      }
     }
     // ragged tail (Sample.cuh:238-252)
     if (kFullChunks >= 1) {
@@ -610,7 +656,11 @@ int
 launch_evaluate(F* functor, const pgn_region_view* v)
 {
   constexpr bool kByValue = pass_by_value<F>::value;
-  if (v == nullptr || v->rule.ndim != NDIM || v->rule.feval != feval_of(NDIM))
+  if (v == nullptr || v->abi_version != PGN_ABI_VERSION || v->view_bytes != sizeof(pgn_region_view)) {
+    std::fprintf(stderr, "pagani_b200: evaluator and libpagani_b200.so were built from different headers\n");
+    return PGN_ERR_INVALID;
+  }
+  if (v->rule.ndim != NDIM || v->rule.feval != feval_of(NDIM))
     return PGN_ERR_INVALID;
   if (v->n == 0)
     return PGN_OK;
@@ -650,6 +700,10 @@ launch_evaluate(F* functor, const pgn_region_view* v)
                         ? static_cast<uint8_t>(host_set_of(first))
                         : static_cast<uint8_t>(0xFF);
     }
+    for (int k = 0; k < 128; ++k)
+      P.chunk_set[k] = (P.half_set[2 * k] != 0xFF && P.half_set[2 * k] == P.half_set[2 * k + 1])
+                         ? P.half_set[2 * k]
+                         : static_cast<uint8_t>(0xFF);
   }
   P.jacobian = v->jacobian;
   P.ratio = v->rule.ratio;

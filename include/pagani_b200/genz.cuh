@@ -278,5 +278,29 @@ struct NotANumber {
 };
 
 }  // namespace testfn
+
+// Launch-bound tuning of the evaluation kernel for the Genz families (B200 sweep of
+// tools/evalbench, profiles/r01_evalbench_*.jsonl): the cos-based family gains a little from 7 resident
+// blocks per SM, the pow()-based ones from 8, the exp-based ones are fastest with registers to spare.
+template <typename F>
+struct EvalTuning;
+#ifndef PGN_EVAL_NO_GENZ_TUNING  // tools/evalbench sweeps the knob through the primary template instead
+template <int N>
+struct EvalTuning<genz::Oscillatory<N>> {
+  static constexpr int kMinBlocks = N <= 8 ? 7 : 4;
+};
+template <int N>
+struct EvalTuning<genz::ProductPeak<N>> {
+  static constexpr int kMinBlocks = 8;
+};
+template <int N>
+struct EvalTuning<genz::CornerPeak<N>> {
+  static constexpr int kMinBlocks = 8;
+};
+template <int N>
+struct EvalTuning<genz::Gaussian<N>> {
+  static constexpr int kMinBlocks = 8;
+};
+#endif
 }  // namespace pagani_b200
 #endif

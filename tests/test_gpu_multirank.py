@@ -45,7 +45,9 @@ def _worker(rank, world, port, out_dir, backend, family, ndim, epsrel, rebalance
         json.dump({"estimate": r.estimate, "errorest": r.errorest, "nregions": r.nregions, "status": r.status,
                    "iters": r.iters, "neval": r.neval,
                    "n_global": [t["nregions_global"] for t in tr], "n_local": [t["nregions"] for t in tr],
-                   "nactive": [t["nactive"] for t in tr], "rebalanced": [t["rebalanced"] for t in tr]}, f)
+                   "nactive": [t["nactive"] for t in tr], "rebalanced": [t["rebalanced"] for t in tr],
+                   "heuristic_ran": [t["heuristic_ran"] for t in tr], "threshold": [t["threshold"] for t in tr],
+                   "heuristic_probes": [t["heuristic_probes"] for t in tr]}, f)
     ws.close()
     import torch.distributed as dist
     dist.barrier()
@@ -106,3 +108,25 @@ def test_nccl_backend_when_two_gpus(pg, tmp_path):
         assert rk["n_global"] == [t["nregions_global"] for t in t1]
         assert (rk["status"], rk["nregions"]) == (r1.status, r1.nregions)
         assert abs(rk["estimate"] - r1.estimate) <= 1e-12 * max(abs(r1.estimate), r1.errorest)
+
+
+def test_nccl_in_kernel_search_follows_single_rank(pg, tmp_path):
+    """Heuristic threshold search with its per-probe all-reduce done INSIDE the kernel over NVLink peer
+    mailboxes (csrc/threshold_search.cuh, k_search<true>): the two ranks must walk through the same probes
+    and accept the same thresholds as the single-rank device search."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ranks = _run(tmp_path, 2, "nccl", 1, 8, 1e-4)
+    r1, t1 = _single(pg, 1, 8, 1e-4)
+    assert any(t["heuristic_ran"] for t in t1)
+    for rk in ranks:
+        assert rk["n_global"] == [t["nregions_global"] for t in t1]
+        assert rk["nactive"] == [t["nactive"] for t in t1]
+        assert rk["heuristic_ran"] == [t["heuristic_ran"] for t in t1]
+        assert rk["heuristic_probes"] == [t["heuristic_probes"] for t in t1]
+        assert rk["threshold"] == pytest.approx([t["threshold"] for t in t1], rel=1e-12)
+        assert (rk["status"], rk["nregions"], rk["iters"]) == (r1.status, r1.nregions, r1.iters)
+        assert abs(rk["estimate"] - r1.estimate) <= 1e-12 * max(abs(r1.estimate), r1.errorest)
+        assert rk["estimate"] == ranks[0]["estimate"] and rk["errorest"] == ranks[0]["errorest"]

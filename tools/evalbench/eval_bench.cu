@@ -27,7 +27,11 @@ main(int argc, char** argv)
   const int parts = argc > 1 ? atoi(argv[1]) : 5;
   const int reps = argc > 2 ? atoi(argv[2]) : 5;
   const int variant = argc > 3 ? atoi(argv[3]) : 0;
+#ifdef BENCH_TESTFN
+  using F = pagani_b200::testfn::BENCH_FAMILY<BENCH_NDIM>;
+#else
   using F = pagani_b200::genz::BENCH_FAMILY<BENCH_NDIM>;
+#endif
   pgn_ctx* ctx = nullptr;
   if (pgn_create(&ctx, BENCH_NDIM, nullptr) != PGN_OK) {
     fprintf(stderr, "pgn_create: %s\n", pgn_last_error());
