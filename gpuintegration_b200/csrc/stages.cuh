@@ -228,7 +228,17 @@ k_classify(const double* __restrict__ est, const double* __restrict__ err_raw,
   __shared__ dev::Acc s_warp[kBlock / 32];
   __shared__ uint64_t s_scan[kBlock];
   const size_t half = n >> 1;
-  const size_t base = static_cast<size_t>(blockIdx.x) * kTile;
+  // Blocks are dispatched in blockIdx order; consecutive blocks take a tile of the left half and the tile
+  // half a list further on, i.e. (nearly) each other's siblings, so the sibling reads of one are the own
+  // reads of the other and hit L2 instead of going to HBM a second time (16.7 M regions: est/err are
+  // 134 MB each, more than L2 holds if the twin tiles run half a grid apart).  Tile-indexed outputs
+  // (partials, tile counts) do not depend on the order tiles are processed in.
+  unsigned int tile = blockIdx.x;
+  if constexpr (REFINE) {
+    const unsigned int first_right = (gridDim.x + 1u) >> 1;
+    tile = (blockIdx.x & 1u) ? first_right + (blockIdx.x >> 1) : (blockIdx.x >> 1);
+  }
+  const size_t base = static_cast<size_t>(tile) * kTile;
   dev::Acc a;
   dev::acc_zero(a);
 #pragma unroll
@@ -271,13 +281,13 @@ k_classify(const double* __restrict__ est, const double* __restrict__ err_raw,
   }
   a = dev::block_reduce(a, s_warp);
   if (threadIdx.x == 0) {
-    double* p = ts.partials + static_cast<size_t>(blockIdx.x) * kStatCount;
+    double* p = ts.partials + static_cast<size_t>(tile) * kStatCount;
 #pragma unroll
     for (int i = 0; i < 5; ++i)
       p[i] = a.v[i];
     p[kMinErr] = a.mn;
     p[kMaxErr] = a.mx;
-    ts.tile_count[blockIdx.x] = static_cast<uint32_t>(a.v[kNumActive]);
+    ts.tile_count[tile] = static_cast<uint32_t>(a.v[kNumActive]);
   }
   dev::finalize(ts, gridDim.x, true, s_warp, s_scan);
 }
@@ -409,55 +419,68 @@ template <bool FUSED>
 __global__ void __launch_bounds__(kBlock)
 k_compact(const CompactArgs A)
 {
-  __shared__ uint32_t s_wsum[kBlock / 32];
+  __shared__ uint32_t s_wsum[kRounds][kBlock / 32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const size_t base = static_cast<size_t>(blockIdx.x) * kTile;
-  uint64_t run = A.tile_offset[blockIdx.x];
   const size_t out_stride = FUSED ? 2 * A.m : A.m;
-#pragma unroll 1
+  // all four rounds' flags first: one barrier per tile, and the loads of different rounds overlap
+  bool on[kRounds];
+  unsigned int ballot[kRounds];
+#pragma unroll
   for (int q = 0; q < kRounds; ++q) {
     const size_t i = base + static_cast<size_t>(q) * kBlock + threadIdx.x;
-    const bool on = i < A.n && A.active[i] != 0;
-    const unsigned int ballot = __ballot_sync(0xffffffffu, on);
+    on[q] = i < A.n && A.active[i] != 0;
+    ballot[q] = __ballot_sync(0xffffffffu, on[q]);
     if (lane == 0)
-      s_wsum[w] = __popc(ballot);
-    __syncthreads();
+      s_wsum[q][w] = __popc(ballot[q]);
+  }
+  __syncthreads();
+  uint64_t run = A.tile_offset[blockIdx.x];
+#pragma unroll
+  for (int q = 0; q < kRounds; ++q) {
     uint32_t before = 0, total = 0;
 #pragma unroll
     for (int k = 0; k < kBlock / 32; ++k) {
-      const uint32_t c = s_wsum[k];
+      const uint32_t c = s_wsum[q][k];
       before += k < w ? c : 0;
       total += c;
     }
-    __syncthreads();
-    if (on) {
-      const size_t j = run + before + __popc(ballot & ((1u << lane) - 1u));
+    if (on[q]) {
+      const size_t i = base + static_cast<size_t>(q) * kBlock + threadIdx.x;
+      const size_t j = run + before + __popc(ballot[q] & ((1u << lane) - 1u));
       const int ax = A.axis[i];
       A.parent_est[j] = A.est[i];
       A.parent_err[j] = A.err[i];
       if (!FUSED)
         A.out_axis[j] = ax;
-      for (int d = 0; d < A.ndim; ++d) {
-        const double lo = A.left[static_cast<size_t>(d) * A.n + i];
-        const double ln = A.length[static_cast<size_t>(d) * A.n + i];
-        double* ol = A.out_left + static_cast<size_t>(d) * out_stride;
-        double* ow = A.out_length + static_cast<size_t>(d) * out_stride;
-        if (FUSED) {
-          if (d == ax) {
-            const double h = __ddiv_rn(ln, 2.0);   // Sub_region_splitter.cuh:33-35
-            ol[j] = lo;
-            ol[A.m + j] = __dadd_rn(lo, h);        // left + 1 * interval_length
-            ow[j] = h;
-            ow[A.m + j] = h;
-          } else {
-            ol[j] = lo;
-            ol[A.m + j] = lo;
-            ow[j] = ln;
-            ow[A.m + j] = ln;
+      // four axes at a time: eight independent loads in flight per thread before the first store
+      // (the output pointers may alias the inputs as far as the compiler knows)
+      for (int d0 = 0; d0 < A.ndim; d0 += 4) {
+        double lo[4], ln[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int d = d0 + k < A.ndim ? d0 + k : A.ndim - 1;
+          lo[k] = __ldcs(&A.left[static_cast<size_t>(d) * A.n + i]);
+          ln[k] = __ldcs(&A.length[static_cast<size_t>(d) * A.n + i]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int d = d0 + k;
+          if (d < A.ndim) {
+            double* ol = A.out_left + static_cast<size_t>(d) * out_stride;
+            double* ow = A.out_length + static_cast<size_t>(d) * out_stride;
+            if (FUSED) {
+              const bool cut = d == ax;
+              const double h = cut ? __ddiv_rn(ln[k], 2.0) : ln[k];  // Sub_region_splitter.cuh:33-35
+              ol[j] = lo[k];
+              ol[A.m + j] = cut ? __dadd_rn(lo[k], h) : lo[k];      // left + 1 * interval_length
+              ow[j] = h;
+              ow[A.m + j] = h;
+            } else {
+              ol[j] = lo[k];
+              ow[j] = ln[k];
+            }
           }
-        } else {
-          ol[j] = lo;
-          ow[j] = ln;
         }
       }
     }

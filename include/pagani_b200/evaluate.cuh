@@ -82,6 +82,19 @@ apply(F& f, const double (&x)[N])
   return apply_impl(f, x, std::make_index_sequence<N>());
 }
 
+// Optional functor protocol: a functor may expose
+//     void pair(const double (&xa)[N], const double (&xb)[N], double& fa, double& fb) const
+// returning exactly operator()(xa...) and operator()(xb...).  The point loop evaluates the two points a
+// lane owns in a chunk through it, which lets an integrand share its rare slow paths between the two
+// (see genz::Oscillatory) so that the common paths interleave.
+template <class F, int N, class = void>
+struct has_pair : std::false_type {};
+template <class F, int N>
+struct has_pair<F, N,
+                std::void_t<decltype(std::declval<const F&>().pair(
+                  std::declval<const double (&)[N]>(), std::declval<const double (&)[N]>(),
+                  std::declval<double&>(), std::declval<double&>()))>> : std::true_type {};
+
 struct EvalParams {
   const double* left;
   const double* length;
@@ -574,6 +587,24 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
       const double fv = apply<F, NDIM>(*fptr, x);
       return __dmul_rn(fv, jac);
     };
+    // the same for the two points a lane owns in a full chunk
+    auto point_values2 = [&](int pa, int pb, double& fa, double& fb) {
+      if constexpr (has_pair<F, NDIM>::value && L::kCodeWords == 2) {
+        const uint2 va = *reinterpret_cast<const uint2*>(s_codes + 2 * pa);
+        const uint2 vb = *reinterpret_cast<const uint2*>(s_codes + 2 * pb);
+        const Words4 ca{va.x, va.y, 0u, 0u}, cb{vb.x, vb.y, 0u, 0u};
+        double xa[NDIM], xb[NDIM];
+        BpGather<NDIM, 0>::run(ca, xbase, xa);
+        BpGather<NDIM, 0>::run(cb, xbase, xb);
+        double va_f, vb_f;
+        static_cast<const F*>(fptr)->pair(xa, xb, va_f, vb_f);
+        fa = __dmul_rn(va_f, jac);
+        fb = __dmul_rn(vb_f, jac);
+      } else {
+        fa = point_value(pa);
+        fb = point_value(pb);
+      }
+    };
     auto accumulate = [&](double (&sum)[PGN_NRULES], double fun, const double* w) {
       sum[0] = __fma_rn(fun, w[0], sum[0]);
       sum[1] = __fma_rn(fun, w[1], sum[1]);
@@ -619,8 +650,8 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
 #pragma unroll 1
           do {
             const int q = k << 6;
-            const double fa = point_value(q + lane);
-            const double fb = point_value(q + 32 + lane);
+            double fa, fb;
+            point_values2(q + lane, q + 32 + lane, fa, fb);
             accumulate(sa, fa, w);
             accumulate(sb, fb, w);
             ++k;

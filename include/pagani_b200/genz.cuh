@@ -16,6 +16,16 @@
 
 #include <cmath>
 
+#include "fastmath.cuh"
+
+// PGN_GENZ_LIBRARY_MATH: call the CUDA math library directly (what the reference's functors do; used by
+// the machine-code parity test); default: the bit-identical, load-free re-expressions of fastmath.cuh
+#ifdef PGN_GENZ_LIBRARY_MATH
+#define PGN_GENZ_COS(x) cos(x)
+#else
+#define PGN_GENZ_COS(x) ::pagani_b200::fastmath::cos_pinned(x)
+#endif
+
 #ifdef __CUDACC__
 #define PGN_HD __host__ __device__
 #else
@@ -59,8 +69,22 @@ struct Oscillatory {
 #pragma unroll
     for (int k = 1; k < N; ++k)
       s = s + static_cast<double>(k + 1) * x[k];
-    return cos(s);
+    return PGN_GENZ_COS(s);
   }
+#if defined(__CUDACC__) && !defined(PGN_GENZ_LIBRARY_MATH) && !defined(PGN_GENZ_NO_PAIR)
+  // two points at once (evaluate.cuh: has_pair): same values as two calls, one shared cold branch
+  __device__ void
+  pair(const double (&xa)[N], const double (&xb)[N], double& fa, double& fb) const
+  {
+    double sa = xa[0], sb = xb[0];
+#pragma unroll
+    for (int k = 1; k < N; ++k) {
+      sa = sa + static_cast<double>(k + 1) * xa[k];
+      sb = sb + static_cast<double>(k + 1) * xb[k];
+    }
+    ::pagani_b200::fastmath::cos_pinned2(sa, sb, fa, fb);
+  }
+#endif
 };
 
 // F_2: prod_k 1 / (a^-2 + (x_k - b)^2),  a = 50, b = .5

@@ -109,6 +109,9 @@ def signatures(tmp_path_factory):
     cu.write_text("\n".join(src))
     subprocess.check_call(["nvcc", "-std=c++17", "-O3", "--expt-relaxed-constexpr", "-gencode",
                            "arch=compute_100a,code=sm_100a", "-I" + REFERENCE, "-I" + os.path.join(ROOT, "include"),
+                           # the math-library spelling of the functors: fastmath.cuh's load-free cos is pinned
+                           # against cos() bit for bit on the GPU instead (tests/test_gpu_fastmath.py)
+                           "-DPGN_GENZ_LIBRARY_MATH",
                            "-w", "-cubin", "-o", str(d / "functors.cubin"), str(cu)])
     sass = subprocess.check_output(["cuobjdump", "-sass", str(d / "functors.cubin")], text=True)
     return _signatures(sass)
