@@ -151,9 +151,12 @@ __device__ __forceinline__ void
 finalize(const TileScratch& ts, unsigned int tiles, bool with_offsets, Acc* s_warp, uint64_t* s_scan)
 {
   __shared__ bool s_last;
-  __threadfence();
-  if (threadIdx.x == 0)
+  // only thread 0's stores (the tile partial and the tile count) are read by the last block: the fence
+  // belongs to that thread alone, the other threads' region outputs need no ordering before kernel end
+  if (threadIdx.x == 0) {
+    __threadfence();
     s_last = atomicAdd(ts.done, 1u) == tiles - 1;
+  }
   __syncthreads();
   if (!s_last)
     return;
@@ -241,20 +244,35 @@ k_classify(const double* __restrict__ est, const double* __restrict__ err_raw,
   const size_t base = static_cast<size_t>(tile) * kTile;
   dev::Acc a;
   dev::acc_zero(a);
+  // all loads of the four rounds first (clamped indices, so they are unconditional): 20 independent
+  // loads in flight per thread instead of four exposed round trips
+  double v_est[kRounds], v_err[kRounds], v_sib_est[kRounds], v_sib_err[kRounds], v_par[kRounds];
+#pragma unroll
+  for (int q = 0; q < kRounds; ++q) {
+    size_t i = base + static_cast<size_t>(q) * kBlock + threadIdx.x;
+    i = i < n ? i : n - 1;
+    v_est[q] = est[i];
+    v_err[q] = err_raw[i];
+    if constexpr (REFINE) {
+      const bool right = (i + i) >= n;
+      const size_t sib = right ? i - half : i + half;
+      const size_t par = right ? i - half : i;
+      v_sib_est[q] = est[sib];
+      v_sib_err[q] = err_raw[sib];
+      v_par[q] = parent_est[par];
+    }
+  }
 #pragma unroll
   for (int q = 0; q < kRounds; ++q) {
     const size_t i = base + static_cast<size_t>(q) * kBlock + threadIdx.x;
     if (i < n) {
-      const double self_est = est[i];
-      double e = err_raw[i];
+      const double self_est = v_est[q];
+      double e = v_err[q];
       double flag = 1.0;
       if constexpr (REFINE) {
-        const bool right = (i + i) >= n;
-        const size_t sib = right ? i - half : i + half;
-        const size_t par = right ? i - half : i;
-        const double sib_est = est[sib];
-        const double sib_err = err_raw[sib];
-        const double par_est = parent_est[par];
+        const double sib_est = v_sib_est[q];
+        const double sib_err = v_sib_err[q];
+        const double par_est = v_par[q];
         // Phases.cuh:251-261 with the rounding sequence of the reference's machine code
         const double diff = fabs(__dmul_rn(__dsub_rn(__dadd_rn(self_est, sib_est), par_est), 0.25));
         const double both = __dadd_rn(e, sib_err);

@@ -51,6 +51,10 @@ constexpr int kWarpsPerBlock = PGN_EVAL_WARPS;
 #ifndef PGN_EVAL_MIN_BLOCKS
 #define PGN_EVAL_MIN_BLOCKS 4
 #endif
+// two chunks (four points per lane) per trip of the point loop inside a run of single-set chunks
+#ifndef PGN_EVAL_QUAD
+#define PGN_EVAL_QUAD 1
+#endif
 
 // Launch-bound tuning knob of the evaluation kernel: resident 128-thread blocks per SM the register
 // allocation must allow (4 -> up to 128 registers per thread, 7 -> 72, 8 -> 64).  Cheap integrands
@@ -83,17 +87,18 @@ apply(F& f, const double (&x)[N])
 }
 
 // Optional functor protocol: a functor may expose
-//     void pair(const double (&xa)[N], const double (&xb)[N], double& fa, double& fb) const
-// returning exactly operator()(xa...) and operator()(xb...).  The point loop evaluates the two points a
-// lane owns in a chunk through it, which lets an integrand share its rare slow paths between the two
-// (see genz::Oscillatory) so that the common paths interleave.
-template <class F, int N, class = void>
-struct has_pair : std::false_type {};
-template <class F, int N>
-struct has_pair<F, N,
-                std::void_t<decltype(std::declval<const F&>().pair(
-                  std::declval<const double (&)[N]>(), std::declval<const double (&)[N]>(),
-                  std::declval<double&>(), std::declval<double&>()))>> : std::true_type {};
+//     template <int M> void batch(const double (&x)[M][N], double (&f)[M]) const
+// returning f[m] == operator()(x[m][0], ..., x[m][N-1]) exactly.  The point loop evaluates the M = 2 or 4
+// points a lane owns in one or two chunks through it, which lets an integrand share its rare slow paths
+// between them (see genz::Oscillatory) so that the common paths are one straight-line block the compiler
+// interleaves: the loop is bound by dependent-issue latency, not by any pipe.
+template <class F, int N, int M, class = void>
+struct has_batch : std::false_type {};
+template <class F, int N, int M>
+struct has_batch<F, N, M,
+                 std::void_t<decltype(std::declval<const F&>().template batch<M>(
+                   std::declval<const double (&)[M][N]>(), std::declval<double (&)[M]>()))>>
+  : std::true_type {};
 
 struct EvalParams {
   const double* left;
@@ -587,22 +592,27 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
       const double fv = apply<F, NDIM>(*fptr, x);
       return __dmul_rn(fv, jac);
     };
-    // the same for the two points a lane owns in a full chunk
-    auto point_values2 = [&](int pa, int pb, double& fa, double& fb) {
-      if constexpr (has_pair<F, NDIM>::value && L::kCodeWords == 2) {
-        const uint2 va = *reinterpret_cast<const uint2*>(s_codes + 2 * pa);
-        const uint2 vb = *reinterpret_cast<const uint2*>(s_codes + 2 * pb);
-        const Words4 ca{va.x, va.y, 0u, 0u}, cb{vb.x, vb.y, 0u, 0u};
-        double xa[NDIM], xb[NDIM];
-        BpGather<NDIM, 0>::run(ca, xbase, xa);
-        BpGather<NDIM, 0>::run(cb, xbase, xb);
-        double va_f, vb_f;
-        static_cast<const F*>(fptr)->pair(xa, xb, va_f, vb_f);
-        fa = __dmul_rn(va_f, jac);
-        fb = __dmul_rn(vb_f, jac);
+    // the same for M points at once: p[m] are the lane's points, f[m] = f(x_p[m]) * Jacobian
+    auto point_values = [&](auto m_tag, const int (&p)[decltype(m_tag)::value],
+                            double (&f)[decltype(m_tag)::value]) {
+      constexpr int M = decltype(m_tag)::value;
+      if constexpr (has_batch<F, NDIM, M>::value && L::kCodeWords == 2) {
+        double x[M][NDIM];
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+          const uint2 v = *reinterpret_cast<const uint2*>(s_codes + 2 * p[m]);
+          const Words4 cw{v.x, v.y, 0u, 0u};
+          BpGather<NDIM, 0>::run(cw, xbase, x[m]);
+        }
+        double fv[M];
+        static_cast<const F*>(fptr)->template batch<M>(x, fv);
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+          f[m] = __dmul_rn(fv[m], jac);
       } else {
-        fa = point_value(pa);
-        fb = point_value(pb);
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+          f[m] = point_value(p[m]);
       }
     };
     auto accumulate = [&](double (&sum)[PGN_NRULES], double fun, const double* w) {
@@ -630,14 +640,30 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
       accumulate(sum, fun, w);
     };
 
+    // per-lane rule weights of point p in the half-chunk starting at q (uniform for most half-chunks)
+    auto lane_weights = [&](int q, int p) -> const double* {
+      int set = P.half_set[q >> 5];
+      if (set == 0xFF)
+        set = s_set[p];
+      return P.wc + set * PGN_NRULES;
+    };
     // chunk 0 keeps its function values for the fourth differences (Sample.cuh:176-219)
-    {
+    if constexpr (kFeval >= 64) {
+      const int p[2] = {lane, lane + 32};
+      double f[2];
+      point_values(std::integral_constant<int, 2>{}, p, f);
+      s_f[lane] = f[0];
+      s_f[lane + 32] = f[1];
+      accumulate(sa, f[0], lane_weights(0, lane));
+      accumulate(sb, f[1], lane_weights(32, lane + 32));
+    } else {
       eval_point(0, lane, sa, true, lane);
       if (lane + 32 < kFeval)
         eval_point(32, lane + 32, sb, true, lane + 32);
     }
     // full chunks: both emulated threads of every lane are busy.  Runs of chunks whose 64 points all
-    // belong to one generator set (most of them) keep the five weights in (uniform) registers.
+    // belong to one generator set (most of them) keep the five weights in (uniform) registers and take
+    // two chunks -- four points per lane -- per trip while the run lasts.
     {
       int k = 1;
 #pragma unroll 1
@@ -650,16 +676,31 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
 #pragma unroll 1
           do {
             const int q = k << 6;
-            double fa, fb;
-            point_values2(q + lane, q + 32 + lane, fa, fb);
-            accumulate(sa, fa, w);
-            accumulate(sb, fb, w);
-            ++k;
+            if (PGN_EVAL_QUAD && k + 1 < kFullChunks && P.chunk_set[k + 1] == st) {
+              const int p[4] = {q + lane, q + 32 + lane, q + 64 + lane, q + 96 + lane};
+              double f[4];
+              point_values(std::integral_constant<int, 4>{}, p, f);
+              accumulate(sa, f[0], w);
+              accumulate(sb, f[1], w);
+              accumulate(sa, f[2], w);
+              accumulate(sb, f[3], w);
+              k += 2;
+            } else {
+              const int p[2] = {q + lane, q + 32 + lane};
+              double f[2];
+              point_values(std::integral_constant<int, 2>{}, p, f);
+              accumulate(sa, f[0], w);
+              accumulate(sb, f[1], w);
+              ++k;
+            }
           } while (k < kFullChunks && P.chunk_set[k] == st);
         } else {
           const int q = k << 6;
-          eval_point(q, q + lane, sa, false, 0);
-          eval_point(q + 32, q + 32 + lane, sb, false, 0);
+          const int p[2] = {q + lane, q + 32 + lane};
+          double f[2];
+          point_values(std::integral_constant<int, 2>{}, p, f);
+          accumulate(sa, f[0], lane_weights(q, p[0]));
+          accumulate(sb, f[1], lane_weights(q + 32, p[1]));
           ++k;
         }
       }

@@ -71,18 +71,21 @@ struct Oscillatory {
       s = s + static_cast<double>(k + 1) * x[k];
     return PGN_GENZ_COS(s);
   }
-#if defined(__CUDACC__) && !defined(PGN_GENZ_LIBRARY_MATH) && !defined(PGN_GENZ_NO_PAIR)
-  // two points at once (evaluate.cuh: has_pair): same values as two calls, one shared cold branch
+#if defined(__CUDACC__) && !defined(PGN_GENZ_LIBRARY_MATH) && !defined(PGN_GENZ_NO_BATCH)
+  // M points at once (evaluate.cuh: has_batch): the same values as M calls, one shared cold branch
+  template <int M>
   __device__ void
-  pair(const double (&xa)[N], const double (&xb)[N], double& fa, double& fb) const
+  batch(const double (&x)[M][N], double (&f)[M]) const
   {
-    double sa = xa[0], sb = xb[0];
+    double s[M];
 #pragma unroll
-    for (int k = 1; k < N; ++k) {
-      sa = sa + static_cast<double>(k + 1) * xa[k];
-      sb = sb + static_cast<double>(k + 1) * xb[k];
+    for (int m = 0; m < M; ++m) {
+      s[m] = x[m][0];
+#pragma unroll
+      for (int k = 1; k < N; ++k)
+        s[m] = s[m] + static_cast<double>(k + 1) * x[m][k];
     }
-    ::pagani_b200::fastmath::cos_pinned2(sa, sb, fa, fb);
+    ::pagani_b200::fastmath::cos_pinned_n<M>(s, f);
   }
 #endif
 };
@@ -311,7 +314,7 @@ struct EvalTuning;
 #ifndef PGN_EVAL_NO_GENZ_TUNING  // tools/evalbench sweeps the knob through the primary template instead
 template <int N>
 struct EvalTuning<genz::Oscillatory<N>> {
-  static constexpr int kMinBlocks = N <= 8 ? 7 : 4;
+  static constexpr int kMinBlocks = 4;
 };
 template <int N>
 struct EvalTuning<genz::ProductPeak<N>> {

@@ -1,4 +1,4 @@
-"""include/pagani_b200/fastmath.cuh: cos_pinned / cos_pinned2 must return the CUDA math library's
+"""include/pagani_b200/fastmath.cuh: cos_pinned / cos_pinned_n must return the CUDA math library's
 cos(double) bit for bit (the Genz oscillatory functor is built on it, and region-trajectory parity with
 the reference needs f(x) bit-identical).  The comparison runs on the GPU (tests/cpp/test_fastmath.cu,
 built by __graft_entry__.build()) over random, near-k*pi/2, boundary, huge and special inputs."""
