@@ -100,6 +100,26 @@ struct has_batch<F, N, M,
                    std::declval<const double (&)[M][N]>(), std::declval<double (&)[M]>()))>>
   : std::true_type {};
 
+// f[m] = functor(x[m]...) for m < M: through the batch protocol when the functor has it
+template <class F, int N, int M, bool HAS = has_batch<F, N, M>::value>
+struct BatchCall {
+  __device__ __forceinline__ static void
+  run(F* f, const double (&x)[M][N], double (&out)[M])
+  {
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+      out[m] = apply<F, N>(*f, x[m]);
+  }
+};
+template <class F, int N, int M>
+struct BatchCall<F, N, M, true> {
+  __device__ __forceinline__ static void
+  run(F* f, const double (&x)[M][N], double (&out)[M])
+  {
+    static_cast<const F*>(f)->template batch<M>(x, out);
+  }
+};
+
 struct EvalParams {
   const double* left;
   const double* length;
@@ -555,6 +575,9 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
   F* fptr = farg.get();
 
   constexpr int kFullChunks = kFeval >> 6;
+  // four-point trips only pay for integrands that take them as one batch (otherwise the second pair's
+  // coordinates just add register pressure)
+  constexpr bool kQuadTrips = PGN_EVAL_QUAD != 0 && has_batch<F, NDIM, 4>::value && L::kCodeWords == 2;
   const double jac = P.jacobian;
   const double ratio = P.ratio;
   const double one_minus_ratio = __dsub_rn(1.0, ratio);
@@ -605,7 +628,7 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
           BpGather<NDIM, 0>::run(cw, xbase, x[m]);
         }
         double fv[M];
-        static_cast<const F*>(fptr)->template batch<M>(x, fv);
+        BatchCall<F, NDIM, M>::run(fptr, x, fv);
 #pragma unroll
         for (int m = 0; m < M; ++m)
           f[m] = __dmul_rn(fv[m], jac);
@@ -676,7 +699,7 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
 #pragma unroll 1
           do {
             const int q = k << 6;
-            if (PGN_EVAL_QUAD && k + 1 < kFullChunks && P.chunk_set[k + 1] == st) {
+            if (kQuadTrips && k + 1 < kFullChunks && P.chunk_set[k + 1] == st) {
               const int p[4] = {q + lane, q + 32 + lane, q + 64 + lane, q + 96 + lane};
               double f[4];
               point_values(std::integral_constant<int, 4>{}, p, f);
