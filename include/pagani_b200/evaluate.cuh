@@ -51,9 +51,11 @@ constexpr int kWarpsPerBlock = PGN_EVAL_WARPS;
 #ifndef PGN_EVAL_MIN_BLOCKS
 #define PGN_EVAL_MIN_BLOCKS 4
 #endif
-// two chunks (four points per lane) per trip of the point loop inside a run of single-set chunks
+// 1: two chunks (four points per lane) per trip of the point loop inside a run of single-set chunks.
+// Measured on B200 (profiles/r01_cos_sweep2.jsonl): no gain over two-point trips -- the loop is bound by
+// issue slots (an FP64 instruction holds the port for two cycles), not by dependent-issue latency.
 #ifndef PGN_EVAL_QUAD
-#define PGN_EVAL_QUAD 1
+#define PGN_EVAL_QUAD 0
 #endif
 
 // Launch-bound tuning knob of the evaluation kernel: resident 128-thread blocks per SM the register
