@@ -1179,6 +1179,7 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
   const double min_err = -host_global_[kNegMinSlot];
   const double max_err = host_global_[kMaxSlot];
   const bool multi = comm_ && comm_->nranks > 1;
+  static const bool search_debug = std::getenv("PGN_SEARCH_DEBUG") != nullptr;
 
   double range_lo = min_err, range_hi = max_err;
   double threshold = iter_err / static_cast<double>(n_global);
@@ -1188,6 +1189,10 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
   double finished_errorest = 0.;
   double active_err_sum = 0.;
   size_t increases = 0, decreases = 0;
+  // threshold of the last probe: the flags the reference adopts are those of its last apply_threshold
+  // call, even when the exhausted-attempts branch resets `threshold` after that probe succeeded
+  // (heuristic_classifier.cuh:404-437, Workspace.cuh:104-106)
+  double applied_threshold = threshold;
 
   // Device-side search: partition the errors into value buckets once, then either run the whole
   // bisection in one kernel (single rank) or answer every probe from the tables (several ranks).
@@ -1235,6 +1240,7 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
     if (h->probes >= 0 && (multi || *h_outside == 0)) {
       searched = true;
       threshold = h->threshold;
+      applied_threshold = h->applied_threshold;
       active_err_sum = h->active_err_sum;
       finished_errorest = h->extra_finished_errorest;
       num_active = static_cast<size_t>(h->num_active);
@@ -1248,6 +1254,7 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
 
   bool first_probe = true;
   auto probe = [&]() -> int {
+    applied_threshold = threshold;
     if (fast) {
       ++launches_, k_query<<<1, kSearchBlock, 0, stream_>>>(threshold, plan, tables,
                                                    stats_dev_.as<double>() + kNumActive,
@@ -1272,6 +1279,10 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
     out->probes++;
     num_active = static_cast<size_t>(host_global_[kNumActive]);
     active_err_sum = host_global_[kSumActErr];
+    if (search_debug)
+      std::fprintf(stderr, "[pgn probe] thr=%.17g active=%zu active_err=%.17g extra=%.17g quarter_budget=%.17g\n", threshold,
+                   num_active, active_err_sum, iter_err - active_err_sum - fin_err,
+                   max_percent_error_budget_ * (target_error - cum_err));
     const double pct =
       static_cast<double>(static_cast<int>(num_active)) / static_cast<double>(static_cast<int>(n_global));
     pass_mem = pct <= max_active_regions_percentage_;
@@ -1325,13 +1336,20 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
   max_active_regions_percentage_ = .5;
   max_percent_error_budget_ = .25;
 
+  if (search_debug) {
+    std::fprintf(stderr, "[pgn search] %s n=%zu iter_err=%.17g fin_err=%.17g cum_err=%.17g target=%.17g min=%.17g max=%.17g"
+                         " -> thr=%.17g applied=%.17g active=%zu active_err=%.17g extra=%.17g pass_mem=%d pass_budget=%d probes=%d\n",
+                 searched ? "device" : "host", n_global, iter_err, fin_err, cum_err, target_error, min_err, max_err,
+                 threshold, applied_threshold, num_active, active_err_sum, finished_errorest, int(pass_mem), int(pass_budget), out->probes);
+  }
+
   out->success = pass_mem && pass_budget;
   out->num_active = num_active;
   out->finished_errorest = finished_errorest;
-  out->threshold = threshold;
+  out->threshold = applied_threshold;
   if (out->success) {
-    // adopt the threshold flags (Workspace.cuh:104-112)
-    PGN_TRY(run_threshold(1, threshold));
+    // adopt the flags of the last probe (Workspace.cuh:104-112)
+    PGN_TRY(run_threshold(1, applied_threshold));
     PGN_TRY(sync_stats(false));
     out->num_active = static_cast<size_t>(host_global_[kNumActive]);
   }

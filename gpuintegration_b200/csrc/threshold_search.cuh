@@ -380,6 +380,7 @@ struct SearchIO {
   unsigned long long seq_base;  // probes exchanged so far on this mailbox (several ranks)
   // out
   double threshold, active_err_sum, extra_finished_errorest;
+  double applied_threshold;  // threshold of the LAST PROBE: the flags the reference ends up with (see k_search)
   unsigned long long num_active;
   int pass_mem, pass_budget;
   int probes;   // -1: a peer did not answer; -2: some rank holds NaN / inf / negative errors
@@ -414,6 +415,11 @@ k_search(BucketPlan plan, BucketTables T, SearchIO* io, PeerBox box)
   double active_err_sum = 0.0, finished_errorest = 0.0;
   unsigned int increases = 0, decreases = 0;
   int probes = 0;
+  // The reference adopts the flag array of its last apply_threshold call (Workspace.cuh:104-106), while
+  // the exhausted-attempts branch below may still reset `threshold` after that probe succeeded (when the
+  // 20th decrease has just been used up): the accepted flags then belong to the last PROBED threshold,
+  // not to the value `threshold` ends with.  Keep both.
+  double applied = threshold;
   unsigned long long seq = in.seq_base;
   const double outside_local = static_cast<double>(*T.outside);
 
@@ -429,6 +435,7 @@ k_search(BucketPlan plan, BucketTables T, SearchIO* io, PeerBox box)
         const unsigned int slot =
           static_cast<unsigned int>((tbits ^ (tbits >> 19) ^ (tbits >> 41)) & (kProbeCache - 1));
         ++probes;
+        applied = threshold;
         if (c_key[slot] == tbits) {
           num_active = c_cnt[slot];
           active_err_sum = c_sum[slot];
@@ -496,6 +503,7 @@ k_search(BucketPlan plan, BucketTables T, SearchIO* io, PeerBox box)
 
   if (threadIdx.x == 0) {
     io->threshold = threshold;
+    io->applied_threshold = applied;
     io->active_err_sum = active_err_sum;
     io->extra_finished_errorest = finished_errorest;
     io->num_active = num_active;

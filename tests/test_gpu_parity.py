@@ -86,7 +86,11 @@ def test_per_region_arrays_match_golden(pg, path):
             assert np.array_equal(axis, z[f"it{it}_axis"]), it
 
 
-LIVE = [(1, 8, 1e-6), (4, 8, 1e-5), (2, 6, 1e-6), (5, 10, 1e-4), (6, 8, 1e-4), (3, 7, 1e-5), (1, 6, 1e-7), (5, 5, 1e-6)]
+# (4, 8, 1e-9) is BASELINE config 5's integrand and tolerance on one GPU: its 17th iteration hits the reference's
+# "search exhausted right after a successful probe" path, where the adopted flags are those of the last probe
+# and not of the (reset) threshold variable (heuristic_classifier.cuh:404-437)
+LIVE = [(1, 8, 1e-6), (4, 8, 1e-5), (2, 6, 1e-6), (5, 10, 1e-4), (6, 8, 1e-4), (3, 7, 1e-5), (1, 6, 1e-7), (5, 5, 1e-6),
+        (4, 8, 1e-9)]
 
 
 @pytest.mark.skipif(not refharness.available(), reason="oracle/_ref/ref_pagani not on this box")

@@ -29,7 +29,7 @@ def run(pg, family, ndim, epsrel, host_search):
 
 # F_1_8D 1e-4: heuristic accepts thresholds and the run converges; 1e-5: ends in a failed search (status 1);
 # F_2_6D 1e-7: BASELINE config 3 (heuristic filter active); F_6_8D: many exactly-zero errors (clamped bucket)
-@pytest.mark.parametrize("family,ndim,epsrel", [(1, 8, 1e-4), (1, 8, 1e-5), (2, 6, 1e-7), (6, 8, 1e-5), (5, 10, 1e-5)])
+@pytest.mark.parametrize("family,ndim,epsrel", [(1, 8, 1e-4), (1, 8, 1e-5), (2, 6, 1e-7), (6, 8, 1e-5), (5, 10, 1e-5), (4, 8, 1e-9)])
 def test_device_search_equals_host_search(pg, family, ndim, epsrel):
     res_d, tr_d = run(pg, family, ndim, epsrel, host_search=False)
     res_h, tr_h = run(pg, family, ndim, epsrel, host_search=True)

@@ -66,6 +66,7 @@ def main():
     ap.add_argument("--out", default="gpurun_out/parity")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--full", type=int, default=0)
+    ap.add_argument("--cases", default="", help='explicit list "family,ndim,epsrel;family,ndim,epsrel;..."')
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
     if a.quick:
@@ -74,6 +75,8 @@ def main():
         cases = [(1, 8, 1e-3), (1, 8, 1e-5), (1, 8, 1e-7), (4, 5, 1e-3), (4, 8, 1e-5), (5, 8, 1e-4),
                  (6, 6, 1e-3), (2, 6, 1e-5), (3, 8, 1e-3), (5, 10, 1e-3), (6, 10, 1e-3), (1, 5, 1e-6),
                  (2, 5, 1e-4), (3, 6, 1e-4), (4, 7, 1e-4), (6, 7, 1e-3)]
+    if a.cases:
+        cases = [(int(c.split(",")[0]), int(c.split(",")[1]), float(c.split(",")[2])) for c in a.cases.split(";") if c]
     ok = True
     with open(os.path.join(a.out, "parity_report.jsonl"), "w") as f:
         for fam, nd, eps in cases:
