@@ -258,10 +258,13 @@ def main():
         "roofline": {"bound": "fp64", "kernel": "pagani_b200::detail::evaluate_kernel_bp<Oscillatory<8>>",
                      "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
                      "traffic": None,
+                     "traffic_note": "ncu --set full, 65536-region launch (profiles/r01_ncu_eval_s8_final.txt): 8.45 MB read, "
+                                     "0 B written back before the kernel ends = 129 B per region for 16*ndim+20 = 148 "
+                                     "algorithmic bytes (part of the bounds is still in L2 from the split kernel)",
                      "note": "ALGORITHMIC flops (SURVEY 8d: 107 per F_1_8D evaluation x 1105 evaluations per region) "
                              "over the CUDA-event time of the evaluation launches of rank 0; peak = FP64 FMA "
                              "micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure); "
-                             "the kernel is FP64/issue bound (arithmetic intensity ~800 flop/B), DRAM traffic not applicable",
+                             "the kernel is FP64/issue bound (arithmetic intensity ~800 flop/B; an FP64 instruction holds the issue port for two cycles, tools/evalbench/fp64_lat.cu), DRAM traffic is negligible",
                      "launches": n_eval_launches, "avg_launch_ms": eval_ms / max(n_eval_launches, 1),
                      "kernel_evals_per_s": local_evals / (eval_ms * 1e-3),
                      "share_of_device_time": eval_ms * 1e-3 / dev_s},
@@ -275,16 +278,29 @@ def main():
         # HBM-bound stages at the largest iteration: classify 29 B/region, fused compact+split (48 ndim + 36) B
         # per surviving region, measured peak from MEASURED_PEAKS.json (driver-written copy bandwidth)
         try:
-            big = max((t for _e, _r, tr in collected for t in tr), key=lambda t: t["nregions"])
             hbm = peaks.get("hbm_gbs") or 6650.0
-            a = big["nactive"] / max(big["nregions"], 1)
-            cls_gbs = 29.0 * big["nregions"] / (big["classify_ms"] * 1e-3) / 1e9 if big["classify_ms"] else None
-            spl_gbs = (48 * NDIM + 36) * big["nactive"] / (big["split_ms"] * 1e-3) / 1e9 if big["split_ms"] else None
+            its = [t for _e, _r, tr in collected for t in tr]
+
+            def stage_roofline(t):
+                a = t["nactive"] / max(t["nregions"], 1)
+                cls = 29.0 * t["nregions"] / (t["classify_ms"] * 1e-3) / 1e9 if t["classify_ms"] else None
+                spl = (48 * NDIM + 36) * t["nactive"] / (t["split_ms"] * 1e-3) / 1e9 if t["split_ms"] else None
+                return {"regions": t["nregions"], "active_fraction": a,
+                        "classify": {"achieved": cls, "frac": cls / hbm if cls else None},
+                        "compact_split": {"achieved": spl, "frac": spl / hbm if spl else None}}
+
+            big = max(its, key=lambda t: t["nregions"])
+            # compaction reads whole 32-byte sectors: with about half the regions surviving (the largest
+            # iteration) most of the dropped regions' bytes are fetched anyway, so the ALGORITHMIC figure
+            # (survivors only) under-states the traffic; the largest iteration in which every region
+            # survives shows the kernel against the roofline without that effect
+            full = [t for t in its if t["nactive"] == t["nregions"] and t["split_ms"]]
             out["roofline_hbm"] = {"bound": "hbm", "unit": "GB/s", "peak": hbm,
                                    "peak_source": "MEASURED_PEAKS.json" if peaks.get("hbm_gbs") else "fallback",
-                                   "regions": big["nregions"], "active_fraction": a,
-                                   "classify": {"achieved": cls_gbs, "frac": cls_gbs / hbm if cls_gbs else None},
-                                   "compact_split": {"achieved": spl_gbs, "frac": spl_gbs / hbm if spl_gbs else None}}
+                                   "bytes_per_region": {"classify": 29, "compact_split_per_survivor": 48 * NDIM + 36},
+                                   **stage_roofline(big)}
+            if full:
+                out["roofline_hbm"]["largest_all_active_iteration"] = stage_roofline(max(full, key=lambda t: t["nregions"]))
         except Exception as e:  # noqa: BLE001
             out["roofline_hbm"] = {"error": repr(e)}
         # CPU baseline: Cuhre (restated) on the host cores, bounded sample

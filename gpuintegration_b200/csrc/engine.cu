@@ -622,14 +622,14 @@ Engine::run_classify(double epsrel, int relerr)
       PGN_TRY(write_empty_stats(stats_dev_.as<double>(), stream_));
     err_cur_ = err_raw_.as<double>();
   } else if (parents_n_ > 0) {
-    ++launches_, k_classify<true><<<tiles_for(n_), kBlock, 0, stream_>>>(
+    ++launches_, k_classify<true><<<super_tiles_for(tiles_for(n_)), kBlock, 0, stream_>>>(
       est_.as<double>(), err_raw_.as<double>(), par_est_[par_cur_].as<double>(),
-      err_ref_.as<double>(), active_.as<uint8_t>(), n_, epsrel, relerr, ts);
+      err_ref_.as<double>(), active_.as<uint8_t>(), n_, epsrel, relerr, static_cast<unsigned int>(tiles_for(n_)), ts);
     err_cur_ = err_ref_.as<double>();
   } else {
-    ++launches_, k_classify<false><<<tiles_for(n_), kBlock, 0, stream_>>>(
+    ++launches_, k_classify<false><<<super_tiles_for(tiles_for(n_)), kBlock, 0, stream_>>>(
       est_.as<double>(), err_raw_.as<double>(), nullptr, nullptr, active_.as<uint8_t>(), n_, epsrel,
-      relerr, ts);
+      relerr, static_cast<unsigned int>(tiles_for(n_)), ts);
     err_cur_ = err_raw_.as<double>();
   }
   PGN_CUDA(cudaGetLastError());

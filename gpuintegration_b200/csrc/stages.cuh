@@ -148,14 +148,17 @@ block_reduce(Acc a, Acc* s_warp /*[kBlock/32]*/)
 // partials in a fixed order, writes the final statistics and the exclusive prefix of the tile
 // counts, and re-arms the counter.
 __device__ __forceinline__ void
-finalize(const TileScratch& ts, unsigned int tiles, bool with_offsets, Acc* s_warp, uint64_t* s_scan)
+finalize(const TileScratch& ts, unsigned int tiles, bool with_offsets, Acc* s_warp, uint64_t* s_scan,
+         unsigned int parts = 0 /* partial records and arriving blocks; 0: one per tile */)
 {
+  if (parts == 0)
+    parts = tiles;
   __shared__ bool s_last;
   // only thread 0's stores (the tile partial and the tile count) are read by the last block: the fence
   // belongs to that thread alone, the other threads' region outputs need no ordering before kernel end
   if (threadIdx.x == 0) {
     __threadfence();
-    s_last = atomicAdd(ts.done, 1u) == tiles - 1;
+    s_last = atomicAdd(ts.done, 1u) == parts - 1;
   }
   __syncthreads();
   if (!s_last)
@@ -163,7 +166,7 @@ finalize(const TileScratch& ts, unsigned int tiles, bool with_offsets, Acc* s_wa
   __threadfence();
   Acc a;
   acc_zero(a);
-  for (unsigned int b = threadIdx.x; b < tiles; b += kBlock) {
+  for (unsigned int b = threadIdx.x; b < parts; b += kBlock) {
     const double* p = ts.partials + static_cast<size_t>(b) * kStatCount;
     Acc t;
 #pragma unroll
@@ -221,93 +224,123 @@ finalize(const TileScratch& ts, unsigned int tiles, bool with_offsets, Acc* s_wa
 // One pass: (optional) two-level error refinement, relative-error flag, all iteration sums.
 // REFINE=false is iteration 0 of the reference loop (no parents yet: hybrid.cuh:26-28 returns
 // early, every region stays active and the raw errors are the errors).
+//
+// A block owns a SUPER-TILE of kSuper consecutive tiles: the per-tile active counts (what compaction
+// needs) come from one __syncthreads_count per tile, the seven statistics are reduced ONCE per block
+// and stored as one partial record per super-tile -- still a fixed shape that depends on n only, so
+// the sums are run-to-run deterministic.  The reduction/arrival tail of a block, during which it has
+// no loads in flight, is thereby paid once per 4096 regions instead of once per 1024.
+constexpr int kSuper = 4;
+__host__ __device__ inline unsigned int
+super_tiles_for(unsigned int tiles)
+{
+  return (tiles + kSuper - 1) / kSuper;
+}
+
 template <bool REFINE>
 __global__ void __launch_bounds__(kBlock)
 k_classify(const double* __restrict__ est, const double* __restrict__ err_raw,
            const double* __restrict__ parent_est, double* __restrict__ err_out,
            uint8_t* __restrict__ active, size_t n, double epsrel, int relerr_classification,
-           TileScratch ts)
+           unsigned int tiles, TileScratch ts)
 {
   __shared__ dev::Acc s_warp[kBlock / 32];
   __shared__ uint64_t s_scan[kBlock];
   const size_t half = n >> 1;
-  // Blocks are dispatched in blockIdx order; consecutive blocks take a tile of the left half and the tile
-  // half a list further on, i.e. (nearly) each other's siblings, so the sibling reads of one are the own
-  // reads of the other and hit L2 instead of going to HBM a second time (16.7 M regions: est/err are
-  // 134 MB each, more than L2 holds if the twin tiles run half a grid apart).  Tile-indexed outputs
-  // (partials, tile counts) do not depend on the order tiles are processed in.
-  unsigned int tile = blockIdx.x;
+  // Blocks are dispatched in blockIdx order; consecutive blocks take a super-tile of the left half and the
+  // one half a list further on, i.e. (nearly) each other's siblings, so the sibling reads of one are the
+  // own reads of the other and hit L2 instead of going to HBM a second time (16.7 M regions: est/err are
+  // 134 MB each).  Tile- and super-tile-indexed outputs do not depend on the processing order.
+  unsigned int sup = blockIdx.x;
   if constexpr (REFINE) {
     const unsigned int first_right = (gridDim.x + 1u) >> 1;
-    tile = (blockIdx.x & 1u) ? first_right + (blockIdx.x >> 1) : (blockIdx.x >> 1);
+    sup = (blockIdx.x & 1u) ? first_right + (blockIdx.x >> 1) : (blockIdx.x >> 1);
   }
-  const size_t base = static_cast<size_t>(tile) * kTile;
+  __shared__ unsigned int s_tile_active[kSuper];
+  if (threadIdx.x < kSuper)
+    s_tile_active[threadIdx.x] = 0u;
+  __syncthreads();
   dev::Acc a;
   dev::acc_zero(a);
-  // all loads of the four rounds first (clamped indices, so they are unconditional): 20 independent
-  // loads in flight per thread instead of four exposed round trips
-  double v_est[kRounds], v_err[kRounds], v_sib_est[kRounds], v_sib_err[kRounds], v_par[kRounds];
+#pragma unroll 1
+  for (int k = 0; k < kSuper; ++k) {
+    const unsigned int tile = sup * kSuper + k;
+    if (tile >= tiles)
+      break;  // uniform over the block
+    const size_t base = static_cast<size_t>(tile) * kTile;
+    // all loads of the four rounds first (clamped indices, so they are unconditional): 20 independent
+    // loads in flight per thread instead of four exposed round trips
+    double v_est[kRounds], v_err[kRounds], v_sib_est[kRounds], v_sib_err[kRounds], v_par[kRounds];
 #pragma unroll
-  for (int q = 0; q < kRounds; ++q) {
-    size_t i = base + static_cast<size_t>(q) * kBlock + threadIdx.x;
-    i = i < n ? i : n - 1;
-    v_est[q] = est[i];
-    v_err[q] = err_raw[i];
-    if constexpr (REFINE) {
-      const bool right = (i + i) >= n;
-      const size_t sib = right ? i - half : i + half;
-      const size_t par = right ? i - half : i;
-      v_sib_est[q] = est[sib];
-      v_sib_err[q] = err_raw[sib];
-      v_par[q] = parent_est[par];
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < kRounds; ++q) {
-    const size_t i = base + static_cast<size_t>(q) * kBlock + threadIdx.x;
-    if (i < n) {
-      const double self_est = v_est[q];
-      double e = v_err[q];
-      double flag = 1.0;
+    for (int q = 0; q < kRounds; ++q) {
+      size_t i = base + static_cast<size_t>(q) * kBlock + threadIdx.x;
+      i = i < n ? i : n - 1;
+      v_est[q] = est[i];
+      v_err[q] = err_raw[i];
       if constexpr (REFINE) {
-        const double sib_est = v_sib_est[q];
-        const double sib_err = v_sib_err[q];
-        const double par_est = v_par[q];
-        // Phases.cuh:251-261 with the rounding sequence of the reference's machine code
-        const double diff = fabs(__dmul_rn(__dsub_rn(__dadd_rn(self_est, sib_est), par_est), 0.25));
-        const double both = __dadd_rn(e, sib_err);
-        if (both > 0.0) {
-          const double c = __dadd_rn(__ddiv_rn(__dadd_rn(diff, diff), both), 1.0);
-          e = __dmul_rn(e, c);
-        }
-        e = __dadd_rn(diff, e);
-        err_out[i] = e;
-        if (relerr_classification) {
-          const double tol = fmax(__dmul_rn(epsrel, fabs(self_est)), 1e-200);
-          flag = (e < tol) ? 0.0 : 1.0;
-        }
+        const bool right = (i + i) >= n;
+        const size_t sib = right ? i - half : i + half;
+        const size_t par = right ? i - half : i;
+        v_sib_est[q] = est[sib];
+        v_sib_err[q] = err_raw[sib];
+        v_par[q] = parent_est[par];
       }
-      active[i] = flag != 0.0 ? 1 : 0;
-      a.v[kSumEst] += self_est;
-      a.v[kSumErr] += e;
-      a.v[kSumActEst] += flag * self_est;  // thrust::inner_product(flags, estimates)
-      a.v[kSumActErr] += flag * e;
-      a.v[kNumActive] += flag;
-      a.mn = fmin(a.mn, e);
-      a.mx = fmax(a.mx, e);
     }
+    int my_active = 0;
+#pragma unroll
+    for (int q = 0; q < kRounds; ++q) {
+      const size_t i = base + static_cast<size_t>(q) * kBlock + threadIdx.x;
+      if (i < n) {
+        const double self_est = v_est[q];
+        double e = v_err[q];
+        double flag = 1.0;
+        if constexpr (REFINE) {
+          const double sib_est = v_sib_est[q];
+          const double sib_err = v_sib_err[q];
+          const double par_est = v_par[q];
+          // Phases.cuh:251-261 with the rounding sequence of the reference's machine code
+          const double diff = fabs(__dmul_rn(__dsub_rn(__dadd_rn(self_est, sib_est), par_est), 0.25));
+          const double both = __dadd_rn(e, sib_err);
+          if (both > 0.0) {
+            const double c = __dadd_rn(__ddiv_rn(__dadd_rn(diff, diff), both), 1.0);
+            e = __dmul_rn(e, c);
+          }
+          e = __dadd_rn(diff, e);
+          err_out[i] = e;
+          if (relerr_classification) {
+            const double tol = fmax(__dmul_rn(epsrel, fabs(self_est)), 1e-200);
+            flag = (e < tol) ? 0.0 : 1.0;
+          }
+        }
+        active[i] = flag != 0.0 ? 1 : 0;
+        my_active += flag != 0.0 ? 1 : 0;
+        a.v[kSumEst] += self_est;
+        a.v[kSumErr] += e;
+        a.v[kSumActEst] += flag * self_est;  // thrust::inner_product(flags, estimates)
+        a.v[kSumActErr] += flag * e;
+        a.v[kNumActive] += flag;
+        a.mn = fmin(a.mn, e);
+        a.mx = fmax(a.mx, e);
+      }
+    }
+    // active regions of this tile: warp sums into a shared counter (integers: order does not matter)
+    const int warp_active = __reduce_add_sync(0xffffffffu, my_active);
+    if ((threadIdx.x & 31) == 0 && warp_active)
+      atomicAdd(&s_tile_active[k], static_cast<unsigned int>(warp_active));
   }
+  __syncthreads();
+  if (threadIdx.x < kSuper && sup * kSuper + threadIdx.x < tiles)
+    ts.tile_count[sup * kSuper + threadIdx.x] = s_tile_active[threadIdx.x];
   a = dev::block_reduce(a, s_warp);
   if (threadIdx.x == 0) {
-    double* p = ts.partials + static_cast<size_t>(tile) * kStatCount;
+    double* p = ts.partials + static_cast<size_t>(sup) * kStatCount;
 #pragma unroll
     for (int i = 0; i < 5; ++i)
       p[i] = a.v[i];
     p[kMinErr] = a.mn;
     p[kMaxErr] = a.mx;
-    ts.tile_count[tile] = static_cast<uint32_t>(a.v[kNumActive]);
   }
-  dev::finalize(ts, gridDim.x, true, s_warp, s_scan);
+  dev::finalize(ts, tiles, true, s_warp, s_scan, gridDim.x);
 }
 
 // One probe of the heuristic threshold search: flag = err > threshold.

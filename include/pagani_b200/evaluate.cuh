@@ -745,6 +745,11 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
   }
 }
 
+template <auto Kernel>
+struct KernelTag {
+  static constexpr auto value = Kernel;
+};
+
 // One instantiation's launch logic (called through the pgn_eval_fn trampoline).  `functor` is the
 // host object when the functor travels by value (nullptr: default-construct it, which is what the
 // pre-instantiated stateless integrands do) and the managed-memory copy otherwise.
@@ -819,8 +824,11 @@ launch_evaluate(F* functor, const pgn_region_view* v)
     }
   }();
 
-  auto launch = [&](auto kernel, size_t smem) -> int {
-    static int blocks_per_sm = 0;  // per instantiation (the lambda is instantiated per kernel)
+  // the kernel is a template ARGUMENT of the tag: the occupancy / attribute cache below is per kernel
+  // (the two point-loop variants have the same function type, so `auto kernel` alone would share it)
+  auto launch = [&](auto tag, size_t smem) -> int {
+    constexpr auto kernel = decltype(tag)::value;
+    static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
       if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(smem)) != cudaSuccess)
@@ -843,9 +851,9 @@ launch_evaluate(F* functor, const pgn_region_view* v)
   constexpr bool kCodesFit = smem_bytes<NDIM>(true) <= 100 * 1024;
   if constexpr (NDIM <= 12) {
     if (v->reserved != kVariantShift)
-      return launch(evaluate_kernel_bp<F, NDIM, kByValue>, BpLayout<NDIM>::bytes());
+      return launch(KernelTag<evaluate_kernel_bp<F, NDIM, kByValue>>{}, BpLayout<NDIM>::bytes());
   }
-  return launch(evaluate_kernel<F, NDIM, kByValue, kCodesFit>, smem_bytes<NDIM>(kCodesFit));
+  return launch(KernelTag<evaluate_kernel<F, NDIM, kByValue, kCodesFit>>{}, smem_bytes<NDIM>(kCodesFit));
 }
 
 template <typename F, int NDIM>
