@@ -299,8 +299,8 @@ Engine::init()
   PGN_CUDA(cudaMallocHost(&host_local_, sizeof(double) * kHostStats));
   PGN_CUDA(cudaMallocHost(&host_global_, sizeof(double) * kHostStats));
   rank_counts_.assign(1, 0);
-  // bucket tables: count, start(+1), cursor, bucket_sum, suffix_sum(+1), suffix_count(+1), outside
-  PGN_TRY(search_tab_.reserve(8 * (6 * static_cast<size_t>(kMaxBuckets) + 8)));
+  // bucket tables: count, start(+1), cursor, bucket_sum, suffix_sum(+1), suffix_count(+1), outside, acc_lo, acc_hi
+  PGN_TRY(search_tab_.reserve(8 * (8 * static_cast<size_t>(kMaxBuckets) + 8)));
   PGN_TRY(search_io_.reserve(sizeof(SearchIO) + 16));
   PGN_CUDA(cudaMallocHost(&host_search_, sizeof(SearchIO) + 16));
   if (const char* hs = std::getenv("PGN_HOST_SEARCH"))
@@ -1105,9 +1105,11 @@ Engine::prepare_search(const BucketPlan& plan, BucketTables* T)
   T->suffix_sum = reinterpret_cast<double*>(base + 4 * nbm + 1);    // nbm + 1
   T->suffix_count = base + 5 * nbm + 2;                              // nbm + 1
   T->outside = base + 6 * nbm + 3;
+  T->acc_lo = base + 6 * nbm + 8;
+  T->acc_hi = base + 7 * nbm + 8;
   PGN_TRY(sorted_err_.reserve(sizeof(double) * std::max<size_t>(n_, 1)));
   T->sorted = sorted_err_.as<double>();
-  PGN_CUDA(cudaMemsetAsync(search_tab_.ptr, 0, 8 * (6 * nbm + 8), stream_));
+  PGN_CUDA(cudaMemsetAsync(search_tab_.ptr, 0, 8 * (8 * nbm + 8), stream_));
   const unsigned grid = static_cast<unsigned>(std::min<size_t>((n_ + kScatterChunk - 1) / kScatterChunk,
                                                                static_cast<size_t>(sm_count_) * 2));
   if (n_ > 0)
@@ -1115,7 +1117,9 @@ Engine::prepare_search(const BucketPlan& plan, BucketTables* T)
   ++launches_, k_bucket_offsets<<<1, kSearchBlock, 0, stream_>>>(plan, *T);
   if (n_ > 0) {
     ++launches_, k_bucket_scatter<<<grid, kSearchBlock, 0, stream_>>>(err_cur_, n_, plan, *T);
-    ++launches_, k_bucket_sums<<<plan.nb, 256, 0, stream_>>>(plan, *T);
+    const unsigned sum_grid = static_cast<unsigned>(std::min<size_t>((n_ + kSumChunk - 1) / kSumChunk,
+                                                                     static_cast<size_t>(sm_count_) * 8));
+    ++launches_, k_bucket_sums<<<sum_grid, kSumThreads, 0, stream_>>>(plan, *T);
   }
   ++launches_, k_bucket_suffix<<<1, kSearchBlock, 0, stream_>>>(plan, *T);
   PGN_CUDA(cudaGetLastError());

@@ -52,6 +52,8 @@ struct BucketTables {
   double* suffix_sum;           // [nb + 1]  sum of buckets b..nb-1, accumulated from the top down
   unsigned long long* suffix_count;  // [nb + 1]
   unsigned long long* outside;  // [1] elements that are not finite non-negative numbers <= max
+  unsigned long long* acc_lo;   // [nb] integer bucket sums (low / high 32-bit pieces), see k_bucket_sums
+  unsigned long long* acc_hi;   // [nb]
   double* sorted;               // [n] the errors grouped by bucket
 };
 
@@ -260,25 +262,74 @@ block_sum3(unsigned long long& a, unsigned long long& b, unsigned long long& c,
   }
 }
 
-// one 256-thread block per bucket: exact sum of the bucket
-__global__ void __launch_bounds__(256)
+// Exact integer sums of the buckets, parallel over ELEMENTS: the error distributions PAGANI produces put most
+// of a list into a handful of buckets, so one block per bucket leaves the device idle.  A block takes chunks of
+// kSumChunk consecutive elements of the bucket-sorted array; a chunk that lies inside one bucket (nearly all of
+// them) is reduced by the block and added with one pair of integer atomics, a chunk that straddles bucket
+// boundaries adds per-thread runs.  Integer additions commute: the totals do not depend on the order.
+constexpr int kSumThreads = 256;
+constexpr int kSumPerThread = 16;
+constexpr int kSumChunk = kSumThreads * kSumPerThread;
+
+__global__ void __launch_bounds__(kSumThreads)
 k_bucket_sums(BucketPlan plan, BucketTables T)
 {
   __shared__ unsigned long long s_red[32][3];
-  for (uint32_t bk = blockIdx.x; bk < plan.nb; bk += gridDim.x) {
-    const unsigned long long lo_i = T.start[bk], hi_i = T.start[bk + 1];
-    const int eref = bucket_exponent(bk, plan);
-    unsigned long long cnt = 0, lo = 0, hi = 0;
-    for (unsigned long long i = lo_i + threadIdx.x; i < hi_i; i += blockDim.x) {
-      const unsigned long long m =
-        scaled_mantissa(static_cast<unsigned long long>(__double_as_longlong(T.sorted[i])), eref);
-      lo += m & 0xffffffffull;
-      hi += m >> 32;
-      ++cnt;
+  const unsigned long long total = T.start[plan.nb];
+  const unsigned long long chunks = (total + kSumChunk - 1) / kSumChunk;
+  for (unsigned long long c = blockIdx.x; c < chunks; c += gridDim.x) {
+    const unsigned long long base = c * kSumChunk;
+    const unsigned long long end = base + kSumChunk < total ? base + kSumChunk : total;
+    const uint32_t b_first = bucket_of(static_cast<unsigned long long>(__double_as_longlong(T.sorted[base])), plan);
+    const uint32_t b_last = bucket_of(static_cast<unsigned long long>(__double_as_longlong(T.sorted[end - 1])), plan);
+    if (b_first == b_last) {  // block-uniform
+      const int eref = bucket_exponent(b_first, plan);
+      unsigned long long cnt = 0, lo = 0, hi = 0;
+#pragma unroll
+      for (int q = 0; q < kSumPerThread; ++q) {
+        const unsigned long long i = base + static_cast<unsigned long long>(q) * kSumThreads + threadIdx.x;
+        if (i < end) {
+          const unsigned long long m =
+            scaled_mantissa(static_cast<unsigned long long>(__double_as_longlong(T.sorted[i])), eref);
+          lo += m & 0xffffffffull;
+          hi += m >> 32;
+        }
+      }
+      block_sum3(cnt, lo, hi, s_red);
+      if (threadIdx.x == 0) {
+        atomicAdd(&T.acc_lo[b_first], lo);
+        atomicAdd(&T.acc_hi[b_first], hi);
+      }
+    } else {
+      // thread t owns elements base + t*16 .. +15: runs of equal bucket, one pair of atomics per run
+      const unsigned long long i0 = base + static_cast<unsigned long long>(threadIdx.x) * kSumPerThread;
+      uint32_t run_b = 0xffffffffu;
+      int eref = 1;
+      unsigned long long lo = 0, hi = 0;
+      for (int q = 0; q < kSumPerThread; ++q) {
+        const unsigned long long i = i0 + q;
+        if (i >= end)
+          break;
+        const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(T.sorted[i]));
+        const uint32_t bb = bucket_of(bits, plan);
+        if (bb != run_b) {
+          if (run_b != 0xffffffffu) {
+            atomicAdd(&T.acc_lo[run_b], lo);
+            atomicAdd(&T.acc_hi[run_b], hi);
+          }
+          run_b = bb;
+          eref = bucket_exponent(bb, plan);
+          lo = hi = 0;
+        }
+        const unsigned long long m = scaled_mantissa(bits, eref);
+        lo += m & 0xffffffffull;
+        hi += m >> 32;
+      }
+      if (run_b != 0xffffffffu) {
+        atomicAdd(&T.acc_lo[run_b], lo);
+        atomicAdd(&T.acc_hi[run_b], hi);
+      }
     }
-    block_sum3(cnt, lo, hi, s_red);
-    if (threadIdx.x == 0)
-      T.bucket_sum[bk] = integer_sum_to_double(lo, hi, eref);
   }
 }
 
@@ -290,8 +341,13 @@ k_bucket_suffix(BucketPlan plan, BucketTables T)
   // thread t owns buckets nb-1-2t and nb-2-2t (descending): local sums, then an inclusive scan
   const int nb = static_cast<int>(plan.nb);
   const int k0 = nb - 1 - 2 * static_cast<int>(threadIdx.x), k1 = k0 - 1;
-  const double v0 = k0 >= 0 ? T.bucket_sum[k0] : 0.0;
-  const double v1 = k1 >= 0 ? T.bucket_sum[k1] : 0.0;
+  // the integer totals of k_bucket_sums, rounded once each
+  const double v0 = k0 >= 0 ? integer_sum_to_double(T.acc_lo[k0], T.acc_hi[k0], bucket_exponent(k0, plan)) : 0.0;
+  const double v1 = k1 >= 0 ? integer_sum_to_double(T.acc_lo[k1], T.acc_hi[k1], bucket_exponent(k1, plan)) : 0.0;
+  if (k0 >= 0)
+    T.bucket_sum[k0] = v0;
+  if (k1 >= 0)
+    T.bucket_sum[k1] = v1;
   s_sum[threadIdx.x] = v0 + v1;
   __syncthreads();
   for (int off = 1; off < kSearchBlock; off <<= 1) {
