@@ -217,6 +217,9 @@ def main():
 
     if rank != 0:
         ws.close()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
         return
 
     fp64_peak = pg.fp64_peak_tflops(local_rank)
@@ -333,7 +336,10 @@ def main():
         except Exception as e:  # noqa: BLE001
             out["reference_gpu"] = {"error": repr(e)}
     ws.close()
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":
