@@ -26,6 +26,21 @@
 #define PGN_GENZ_COS(x) ::pagani_b200::fastmath::cos_pinned(x)
 #endif
 
+// PGN_GENZ_FAST_POW=1: the squares of the product-peak and Gaussian families through fastmath::pow2_pinned_n
+// (the math library's pow(x, 2.) sequence, straight-line).  Off by default until pinned on a GPU.
+#ifndef PGN_GENZ_FAST_POW
+#define PGN_GENZ_FAST_POW 0
+#endif
+#if PGN_GENZ_FAST_POW && !defined(PGN_GENZ_LIBRARY_MATH)
+#define PGN_GENZ_SQUARES(N, d, sq) ::pagani_b200::fastmath::pow2_pinned_n<N>(d, sq)
+#else
+#define PGN_GENZ_SQUARES(N, d, sq)  \
+  do {                              \
+    for (int k_ = 0; k_ < N; ++k_)  \
+      sq[k_] = pow(d[k_], 2.);      \
+  } while (0)
+#endif
+
 #ifdef __CUDACC__
 #define PGN_HD __host__ __device__
 #else
@@ -102,12 +117,26 @@ struct ProductPeak {
     const double x[N] = {xs...};
     const double a = 50.;
     const double b = .5;
+#if PGN_GENZ_FAST_POW && !defined(PGN_GENZ_LIBRARY_MATH)
+    double d[N], sq[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      d[k] = x[k] - b;
+    PGN_GENZ_SQUARES(N, d, sq);
+    double val = 1. / ((1. / pow(a, 2.)) + sq[0]);
+#pragma unroll
+    for (int k = 1; k < N; ++k) {
+      const double term = 1. / ((1. / pow(a, 2.)) + sq[k]);
+      val = val * term;
+    }
+#else
     double val = 1. / ((1. / pow(a, 2.)) + pow(x[0] - b, 2.));
 #pragma unroll
     for (int k = 1; k < N; ++k) {
       const double term = 1. / ((1. / pow(a, 2.)) + pow(x[k] - b, 2.));
       val = val * term;
     }
+#endif
     return val;
   }
 };
@@ -144,10 +173,22 @@ struct Gaussian {
     static_assert(sizeof...(T) == N, "arity");
     const double x[N] = {xs...};
     const double beta = .5;
+#if PGN_GENZ_FAST_POW && !defined(PGN_GENZ_LIBRARY_MATH)
+    double d[N], sq[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      d[k] = x[k] - beta;
+    PGN_GENZ_SQUARES(N, d, sq);
+    double s = pow(25., 2.) * sq[0];
+#pragma unroll
+    for (int k = 1; k < N; ++k)
+      s = s + pow(25., 2.) * sq[k];
+#else
     double s = pow(25., 2.) * pow(x[0] - beta, 2.);
 #pragma unroll
     for (int k = 1; k < N; ++k)
       s = s + pow(25., 2.) * pow(x[k] - beta, 2.);
+#endif
     return exp(-1.0 * s);
   }
 };
