@@ -26,10 +26,11 @@
 #define PGN_GENZ_COS(x) ::pagani_b200::fastmath::cos_pinned(x)
 #endif
 
-// PGN_GENZ_FAST_POW=1: the squares of the product-peak and Gaussian families through fastmath::pow2_pinned_n
-// (the math library's pow(x, 2.) sequence, straight-line).  Off by default until pinned on a GPU.
+// PGN_GENZ_FAST_POW (default 1): the squares of the product-peak and Gaussian families through
+// fastmath::pow2_pinned_n -- the math library's pow(x, 2.) operation sequence as straight-line code, bit-identical
+// to pow(x, 2.) (tests/cpp/test_fastmath.cu) and 21-26 % faster in the evaluation kernel (profiles/r01_pow_sweep.jsonl).
 #ifndef PGN_GENZ_FAST_POW
-#define PGN_GENZ_FAST_POW 0
+#define PGN_GENZ_FAST_POW 1
 #endif
 #if PGN_GENZ_FAST_POW && !defined(PGN_GENZ_LIBRARY_MATH)
 #define PGN_GENZ_SQUARES(N, d, sq) ::pagani_b200::fastmath::pow2_pinned_n<N>(d, sq)
@@ -348,8 +349,9 @@ struct NotANumber {
 }  // namespace testfn
 
 // Launch-bound tuning of the evaluation kernel for the Genz families (B200 sweep of
-// tools/evalbench, profiles/r01_evalbench_*.jsonl): the cos-based family gains a little from 7 resident
-// blocks per SM, the pow()-based ones from 8, the exp-based ones are fastest with registers to spare.
+// tools/evalbench, profiles/r01_evalbench_*.jsonl, r01_cos_sweep2.jsonl, r01_pow_sweep.jsonl): with the pinned,
+// straight-line cos and pow(x, 2.) the oscillatory, Gaussian and product-peak families are fastest with registers
+// to spare (4 / 3 / 4 resident blocks), the corner peak (general pow) with 8.
 template <typename F>
 struct EvalTuning;
 #ifndef PGN_EVAL_NO_GENZ_TUNING  // tools/evalbench sweeps the knob through the primary template instead
@@ -359,7 +361,7 @@ struct EvalTuning<genz::Oscillatory<N>> {
 };
 template <int N>
 struct EvalTuning<genz::ProductPeak<N>> {
-  static constexpr int kMinBlocks = 8;
+  static constexpr int kMinBlocks = PGN_GENZ_FAST_POW ? 4 : 8;
 };
 template <int N>
 struct EvalTuning<genz::CornerPeak<N>> {
@@ -367,7 +369,7 @@ struct EvalTuning<genz::CornerPeak<N>> {
 };
 template <int N>
 struct EvalTuning<genz::Gaussian<N>> {
-  static constexpr int kMinBlocks = 8;
+  static constexpr int kMinBlocks = PGN_GENZ_FAST_POW ? 3 : 8;
 };
 #endif
 }  // namespace pagani_b200
