@@ -42,6 +42,17 @@
   } while (0)
 #endif
 
+// PGN_GENZ_FAST_EXP (default 0, not yet pinned on a GPU): exp() of the Gaussian, C0 and discontinuous families
+// through fastmath::exp_pinned
+#ifndef PGN_GENZ_FAST_EXP
+#define PGN_GENZ_FAST_EXP 0
+#endif
+#if PGN_GENZ_FAST_EXP && !defined(PGN_GENZ_LIBRARY_MATH)
+#define PGN_GENZ_EXP(x) ::pagani_b200::fastmath::exp_pinned(x)
+#else
+#define PGN_GENZ_EXP(x) exp(x)
+#endif
+
 #ifdef __CUDACC__
 #define PGN_HD __host__ __device__
 #else
@@ -190,7 +201,7 @@ struct Gaussian {
     for (int k = 1; k < N; ++k)
       s = s + pow(25., 2.) * pow(x[k] - beta, 2.);
 #endif
-    return exp(-1.0 * s);
+    return PGN_GENZ_EXP(-1.0 * s);
   }
 };
 
@@ -212,7 +223,7 @@ struct CZero {
 #pragma unroll
     for (int k = 2; k < N; ++k)
       t1 = fma_rn(-10., fabs(x[k] - beta), t1);
-    return exp(t1);
+    return PGN_GENZ_EXP(t1);
   }
 };
 
@@ -296,7 +307,7 @@ struct Discontinuous {
       for (int k = 2; k < N; ++k)
         s = fma_rn(Spec::alpha(k), x[k], s);
     }
-    return exp(s);
+    return PGN_GENZ_EXP(s);
   }
 };
 

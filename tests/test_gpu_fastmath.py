@@ -16,4 +16,7 @@ def test_cos_pinned_is_bit_identical_to_library_cos():
     assert os.path.exists(EXE), "tests/cpp/_build/test_fastmath missing: run __graft_entry__.build()"
     p = subprocess.run([EXE, "20000000", "pow"], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout + p.stderr
-    assert "cos variant" in p.stdout and "pow2_pinned: identical" in p.stdout and "MISMATCH" not in p.stdout
+    lines = p.stdout.splitlines()
+    assert any(l.startswith("cos variant") and l.endswith("identical") for l in lines), p.stdout
+    assert "pow2_pinned: identical" in lines, p.stdout
+    # exp_pinned is opt-in and only reported (see fastmath.cuh): not asserted here
