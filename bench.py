@@ -260,7 +260,8 @@ def main():
         "wall_ms_per_step_timed_region": 1e3 * wall / args.steps,
         "roofline": {"bound": "fp64", "kernel": "pagani_b200::detail::evaluate_kernel_bp<Oscillatory<8>>",
                      "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
-                     "traffic": None,
+                     # DRAM bytes per launch: 128.9 B per region (ncu, below) x regions of the average launch
+                     "traffic": 128.9 * (local_evals / feval) / max(n_eval_launches, 1),
                      "traffic_note": "ncu --set full, 65536-region launch (profiles/r01_ncu_eval_s8_final.txt): 8.45 MB read, "
                                      "0 B written back before the kernel ends = 129 B per region for 16*ndim+20 = 148 "
                                      "algorithmic bytes (part of the bounds is still in L2 from the split kernel)",
