@@ -236,6 +236,92 @@ struct Tracker {
   }
 };
 
+
+// Heuristic_classifier::classify (heuristic_classifier.cuh:362-451) on a host array.  The flags left in
+// `flags` are those of the LAST apply_threshold call -- what the reference adopts (Workspace.cuh:104-106) --
+// also when the exhausted-attempts branch has reset `thr` after that probe succeeded.
+struct SearchOut {
+  bool pass_mem = false, pass_budget = false;
+  size_t num_active = 0;
+  double finished_errorest = 0., threshold = 0., budget_pct = .25, active_pct = .5;
+  int probes = 0;
+};
+
+SearchOut
+classify_threshold(const double* err, size_t n, double iter_err, double fin_err, double cum_err, double target,
+                   std::vector<uint8_t>& flags)
+{
+  SearchOut o;
+  double mn = std::numeric_limits<double>::infinity(), mx = -mn;
+  for (size_t i = 0; i < n; ++i) {
+    mn = std::fmin(mn, err[i]);
+    mx = std::fmax(mx, err[i]);
+  }
+  double lo = mn, hi = mx, thr = iter_err / (double)n;
+  double budget_pct = .25, active_pct = .5;
+  bool pass_mem = false, pass_budget = false;
+  size_t cnt = 0, inc = 0, dec = 0;
+  double act_sum = 0, hs_fin = 0;
+  flags.assign(n, 0);
+  auto apply = [&]() {
+    cnt = 0;
+    act_sum = 0;
+    for (size_t i = 0; i < n; ++i) {
+      flags[i] = err[i] > thr;
+      cnt += flags[i];
+      act_sum += flags[i] * err[i];
+    }
+    pass_mem = (double)(int)cnt / (double)(int)n <= active_pct;
+    o.probes++;
+  };
+  do {
+    if (!pass_mem && inc <= 20) {
+      pass_mem = false;
+      size_t attempts = 0;
+      while (!pass_mem && attempts < 20) {
+        apply();
+        if (!pass_mem) {
+          lo = thr;
+          thr += std::fabs(hi - thr) * .5;
+        }
+        attempts++;
+      }
+      inc++;
+    }
+    if (pass_mem) {
+      const double extra = iter_err - act_sum - fin_err;
+      pass_budget = extra <= budget_pct * (target - cum_err);
+      hs_fin = extra;
+      if (!pass_budget && dec <= 20) {
+        hi = thr;
+        thr -= std::fabs(lo - thr) * .5;
+        pass_mem = false;
+        dec++;
+      }
+    }
+    const bool exhausted = dec >= 20 || inc >= 20;
+    if (exhausted && budget_pct < .7) {
+      budget_pct += 0.1;
+      dec = inc = 0;
+      lo = mn;
+      hi = mx;
+      thr = iter_err / (double)n;
+    } else if (exhausted && budget_pct >= .7 && active_pct <= .7) {
+      active_pct += .1;
+    } else if (exhausted) {
+      break;
+    }
+  } while (!pass_mem || !pass_budget);
+  o.pass_mem = pass_mem;
+  o.pass_budget = pass_budget;
+  o.num_active = cnt;
+  o.finished_errorest = hs_fin;
+  o.threshold = thr;
+  o.budget_pct = budget_pct;
+  o.active_pct = active_pct;
+  return o;
+}
+
 }  // namespace
 
 extern "C" {
@@ -301,6 +387,30 @@ orc_refine(const double* est, const double* err_raw, const double* parent_est, u
 // Workspace::integrate (Workspace.cuh:361-494), sequential.  `records` (may be null) receives up to
 // max_records per-iteration summaries.  mem_bytes is the device size the heuristic assumes
 // (16e9 in the reference, heuristic_classifier.cuh:89-94).
+// Heuristic_classifier::classify on a caller-supplied error list (the reference's classifier KAT,
+// test/kokkos/pagani/test_heuristic_classifier.cpp:32-103).  last_estimate is what store_estimate() saw last.
+// out[0..6] = pass_mem, pass_errorest_budget, num_active, finished_errorest, max_budget_perc_to_cover,
+// max_active_perc, probes, threshold (the variable's final value); flags[n] receives the adopted flags.
+void
+orc_classify_threshold(const double* err, uint64_t n, double iter_errorest, double iter_finished_errorest,
+                       double total_finished_errorest, double last_estimate, double epsrel, uint8_t* flags,
+                       double* out)
+{
+  std::vector<uint8_t> f;
+  const SearchOut so = classify_threshold(err, n, iter_errorest, iter_finished_errorest, total_finished_errorest,
+                                          std::fabs(last_estimate) * epsrel, f);
+  for (uint64_t i = 0; i < n; ++i)
+    flags[i] = f[i];
+  out[0] = so.pass_mem;
+  out[1] = so.pass_budget;
+  out[2] = static_cast<double>(so.num_active);
+  out[3] = so.finished_errorest;
+  out[4] = so.budget_pct;
+  out[5] = so.active_pct;
+  out[6] = so.probes;
+  out[7] = so.threshold;
+}
+
 int
 orc_integrate(int family, int ndim, int feval, const double* gens, const double* weights,
               const double* scale, const double* norm, const int32_t* set_of_point, const double* G,
@@ -335,7 +445,6 @@ orc_integrate(int family, int ndim, int feval, const double* gens, const double*
   tracker.epsrel = epsrel;
   tracker.epsabs = epsabs;
   tracker.required_digits = (int)std::ceil(std::log10(1 / epsrel));
-  double budget_pct = .25, active_pct = .5;
 
   std::vector<double> parent_est;
   double cum_est = 0, cum_err = 0;
@@ -429,67 +538,12 @@ orc_integrate(int family, int ndim, int feval, const double* gens, const double*
       } else {
         rec.heuristic_ran = 1;
         // Heuristic_classifier::classify, heuristic_classifier.cuh:362-451
-        double mn = std::numeric_limits<double>::infinity(), mx = -mn;
-        for (size_t i = 0; i < n; ++i) {
-          mn = std::fmin(mn, err[i]);
-          mx = std::fmax(mx, err[i]);
-        }
-        double lo = mn, hi = mx, thr = iter_err / (double)n;
-        const double target = std::fabs(tracker.last[2]) * epsrel;
-        bool pass_mem = false, pass_budget = false;
-        size_t cnt = 0, inc = 0, dec = 0;
-        double act_sum = 0, hs_fin = 0;
-        std::vector<uint8_t> flags(n);
-        auto apply = [&]() {
-          cnt = 0;
-          act_sum = 0;
-          for (size_t i = 0; i < n; ++i) {
-            flags[i] = err[i] > thr;
-            cnt += flags[i];
-            act_sum += flags[i] * err[i];
-          }
-          pass_mem = (double)(int)cnt / (double)(int)n <= active_pct;
-        };
-        do {
-          if (!pass_mem && inc <= 20) {
-            pass_mem = false;
-            size_t attempts = 0;
-            while (!pass_mem && attempts < 20) {
-              apply();
-              if (!pass_mem) {
-                lo = thr;
-                thr += std::fabs(hi - thr) * .5;
-              }
-              attempts++;
-            }
-            inc++;
-          }
-          if (pass_mem) {
-            const double extra = iter_err - act_sum - fin_err;
-            pass_budget = extra <= budget_pct * (target - cum_err);
-            hs_fin = extra;
-            if (!pass_budget && dec <= 20) {
-              hi = thr;
-              thr -= std::fabs(lo - thr) * .5;
-              pass_mem = false;
-              dec++;
-            }
-          }
-          const bool exhausted = dec >= 20 || inc >= 20;
-          if (exhausted && budget_pct < .7) {
-            budget_pct += 0.1;
-            dec = inc = 0;
-            lo = mn;
-            hi = mx;
-            thr = iter_err / (double)n;
-          } else if (exhausted && budget_pct >= .7 && active_pct <= .7) {
-            active_pct += .1;
-          } else if (exhausted) {
-            break;
-          }
-        } while (!pass_mem || !pass_budget);
-        active_pct = .5;
-        budget_pct = .25;
+        std::vector<uint8_t> flags;
+        const SearchOut so = classify_threshold(err.data(), n, iter_err, fin_err, cum_err,
+                                                std::fabs(tracker.last[2]) * epsrel, flags);
+        const bool pass_mem = so.pass_mem, pass_budget = so.pass_budget;
+        const size_t cnt = so.num_active;
+        const double hs_fin = so.finished_errorest;
         const bool success = pass_mem && pass_budget;
         if (success) {
           active = flags;

@@ -110,6 +110,20 @@ def refine(est, err_raw, parent_est, epsrel, relerr=True):
     return out, act
 
 
+def classify_threshold(errors, iter_errorest, iter_finished_errorest, total_finished_errorest, last_estimate, epsrel):
+    """Heuristic_classifier::classify (heuristic_classifier.cuh:362-451) on a host error list."""
+    err = np.ascontiguousarray(errors, dtype=np.float64)
+    flags = np.zeros(len(err), dtype=np.uint8)
+    out = np.zeros(8)
+    lib().orc_classify_threshold(err.ctypes.data_as(_dp), C.c_uint64(len(err)), C.c_double(iter_errorest),
+                                 C.c_double(iter_finished_errorest), C.c_double(total_finished_errorest),
+                                 C.c_double(last_estimate), C.c_double(epsrel),
+                                 flags.ctypes.data_as(C.POINTER(C.c_uint8)), out.ctypes.data_as(_dp))
+    return {"pass_mem": bool(out[0]), "pass_errorest_budget": bool(out[1]), "num_active": int(out[2]),
+            "finished_errorest": out[3], "max_budget_perc_to_cover": out[4], "max_active_perc": out[5],
+            "probes": int(out[6]), "threshold": out[7], "flags": flags}
+
+
 def integrate(family, ndim, epsrel, epsabs=1e-40, lows=None, highs=None, relerr=True, mem_bytes=16e9,
               max_iters=700, max_regions=2_000_000, max_records=800):
     t = Tables(ndim)

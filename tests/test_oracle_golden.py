@@ -139,3 +139,45 @@ def test_cuhre_restated_accuracy():
     assert r8["estimate"] == r["estimate"] and r8["neval"] == r["neval"]  # threading does not change the result
     r = oracle.cuhre(6, 6, 1e-3, threads=0)
     assert r["status"] == 0 and r["estimate"] == pytest.approx(1.5477367885091207413e8, rel=1e-3)
+
+
+def test_heuristic_classifier_kat():
+    """The reference's own classifier known-answer test (test/kokkos/pagani/test_heuristic_classifier.cpp:32-103,
+    "50% mem save prevented by high finished error-estimate"): seven regions, converged estimate 7000, epsrel
+    1e-3, 4.2 of finished error already spent -- the search has to relax both budgets and ends with four regions
+    active."""
+    errors = [.075, .99, .079, 101.96, 101.33, 1.93, 101.99]
+    r = oracle.classify_threshold(errors, iter_errorest=sum(errors), iter_finished_errorest=0.,
+                                      total_finished_errorest=4.2, last_estimate=7000., epsrel=1e-3)
+    saved = 1. - r["num_active"] / len(errors)
+    assert .3 < saved <= .5
+    assert r["pass_errorest_budget"] and r["pass_mem"]
+    assert r["max_budget_perc_to_cover"] > .25 and r["max_active_perc"] > .5
+    # the adopted flags are those of the last probe: exactly the regions above some threshold
+    act = np.array(errors)[r["flags"] == 1]
+    fin = np.array(errors)[r["flags"] == 0]
+    assert len(act) == r["num_active"] and (len(fin) == 0 or act.min() > fin.max())
+    assert r["finished_errorest"] == pytest.approx(fin.sum(), rel=1e-12)
+
+
+def test_heuristic_search_keeps_flags_of_last_probe():
+    """When the search's 20th pass is the one whose probe finally satisfies both budgets, the reference's
+    exhausted-attempts branch still fires (it counts passes), resets the threshold VARIABLE to iter_err / n and
+    relaxes the budget, but the flag array it adopts is the one of that last probe
+    (heuristic_classifier.cuh:404-437, Workspace.cuh:104-106) -- iteration 16 of F_4_8D at epsrel 1e-9 does this
+    on the GPU.  Constructed case: the budget check fails for thresholds t0, ~t0/2, ..., ~t0/2^18 (a group of
+    5e-9 errors gets finished) and passes at ~t0/2^19 = 3.7e-9 (the group stays active)."""
+    n = 4096
+    errors = np.full(n, 1e-12)
+    errors[:8] = 1.0
+    errors[8:2048] = 5e-9
+    iter_err = errors.sum()
+    t0 = iter_err / n
+    tail = errors[2048:].sum()
+    target = 4 * 1.5 * tail                # a quarter of the budget covers the 1e-12 tail, not the 5e-9 group
+    r = oracle.classify_threshold(errors, iter_err, 0., 0., target / 1e-3, 1e-3)
+    assert r["pass_mem"] and r["pass_errorest_budget"] and r["probes"] == 20
+    assert r["threshold"] == t0 and r["max_budget_perc_to_cover"] == pytest.approx(.35)   # variable reset, budget relaxed
+    assert r["num_active"] == 2048 and r["flags"][:2048].all() and not r["flags"][2048:].any()  # flags of the last probe
+    assert (errors > t0).sum() == 8        # what re-applying the reset variable would have kept
+    assert r["finished_errorest"] == pytest.approx(tail, rel=1e-3)
