@@ -621,12 +621,18 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
     auto point_values = [&](auto m_tag, const int (&p)[decltype(m_tag)::value],
                             double (&f)[decltype(m_tag)::value]) {
       constexpr int M = decltype(m_tag)::value;
-      if constexpr (has_batch<F, NDIM, M>::value && L::kCodeWords == 2) {
+      if constexpr (has_batch<F, NDIM, M>::value) {
         double x[M][NDIM];
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-          const uint2 v = *reinterpret_cast<const uint2*>(s_codes + 2 * p[m]);
-          const Words4 cw{v.x, v.y, 0u, 0u};
+          Words4 cw;
+          if constexpr (L::kCodeWords == 2) {
+            const uint2 v = *reinterpret_cast<const uint2*>(s_codes + 2 * p[m]);
+            cw = Words4{v.x, v.y, 0u, 0u};
+          } else {
+            const uint4 v = *reinterpret_cast<const uint4*>(s_codes + 4 * p[m]);
+            cw = Words4{v.x, v.y, v.z, v.w};
+          }
           BpGather<NDIM, 0>::run(cw, xbase, x[m]);
         }
         double fv[M];

@@ -225,6 +225,25 @@ struct CZero {
       t1 = fma_rn(-10., fabs(x[k] - beta), t1);
     return PGN_GENZ_EXP(t1);
   }
+#if defined(__CUDACC__) && PGN_GENZ_FAST_EXP && !defined(PGN_GENZ_LIBRARY_MATH) && !defined(PGN_GENZ_NO_BATCH)
+  // M points at once (evaluate.cuh: has_batch): the same values as M calls, one shared cold branch
+  template <int M>
+  __device__ void
+  batch(const double (&x)[M][N], double (&f)[M]) const
+  {
+    const double beta = .5;
+    double t[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      t[m] = mul_rn(-10., fabs(x[m][1] - beta));
+      t[m] = fma_rn(-10., fabs(x[m][0] - beta), t[m]);
+#pragma unroll
+      for (int k = 2; k < N; ++k)
+        t[m] = fma_rn(-10., fabs(x[m][k] - beta), t[m]);
+    }
+    ::pagani_b200::fastmath::exp_pinned_n<M>(t, f);
+  }
+#endif
 };
 
 // F_6: 0 if any x_k > beta_k, else exp(sum alpha_k x_k).  The reference orders its arguments
@@ -309,6 +328,40 @@ struct Discontinuous {
     }
     return PGN_GENZ_EXP(s);
   }
+#if defined(__CUDACC__) && PGN_GENZ_FAST_EXP && !defined(PGN_GENZ_LIBRARY_MATH) && !defined(PGN_GENZ_NO_BATCH)
+  // M points at once: exponent and exp for every point (harmless for the ones outside), then the zero
+  template <int M>
+  __device__ void
+  batch(const double (&x)[M][N], double (&f)[M]) const
+  {
+    double s[M];
+    bool outside[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      outside[m] = false;
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        outside[m] = outside[m] || (x[m][k] > Spec::beta(k));
+      if (Spec::descending) {
+        s[m] = mul_rn(Spec::alpha(N - 1), x[m][N - 1]);
+#pragma unroll
+        for (int k = N - 2; k >= 0; --k)
+          s[m] = fma_rn(Spec::alpha(k), x[m][k], s[m]);
+      } else {
+        s[m] = mul_rn(Spec::alpha(1), x[m][1]);
+        s[m] = fma_rn(Spec::alpha(0), x[m][0], s[m]);
+#pragma unroll
+        for (int k = 2; k < N; ++k)
+          s[m] = fma_rn(Spec::alpha(k), x[m][k], s[m]);
+      }
+    }
+    double e[M];
+    ::pagani_b200::fastmath::exp_pinned_n<M>(s, e);
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+      f[m] = outside[m] ? 0. : e[m];
+  }
+#endif
 };
 
 }  // namespace genz
