@@ -32,18 +32,9 @@
 #ifndef PGN_GENZ_FAST_POW
 #define PGN_GENZ_FAST_POW 1
 #endif
-#if PGN_GENZ_FAST_POW && !defined(PGN_GENZ_LIBRARY_MATH)
-#define PGN_GENZ_SQUARES(N, d, sq) ::pagani_b200::fastmath::pow2_pinned_n<N>(d, sq)
-#else
-#define PGN_GENZ_SQUARES(N, d, sq)  \
-  do {                              \
-    for (int k_ = 0; k_ < N; ++k_)  \
-      sq[k_] = pow(d[k_], 2.);      \
-  } while (0)
-#endif
-
-// PGN_GENZ_FAST_EXP (default 0, not yet pinned on a GPU): exp() of the Gaussian, C0 and discontinuous families
-// through fastmath::exp_pinned
+// PGN_GENZ_FAST_EXP (default 0): exp() of the Gaussian, C0 and discontinuous families through fastmath::exp_pinned
+// (bit-identical to exp() on the GPU; not the default until the kernels are timed and the parity cases run with it:
+// tools/gpu_exp_check.sh)
 #ifndef PGN_GENZ_FAST_EXP
 #define PGN_GENZ_FAST_EXP 0
 #endif
@@ -134,7 +125,7 @@ struct ProductPeak {
 #pragma unroll
     for (int k = 0; k < N; ++k)
       d[k] = x[k] - b;
-    PGN_GENZ_SQUARES(N, d, sq);
+    ::pagani_b200::fastmath::pow2_pinned_n<N>(d, sq);
     double val = 1. / ((1. / pow(a, 2.)) + sq[0]);
 #pragma unroll
     for (int k = 1; k < N; ++k) {
@@ -190,7 +181,7 @@ struct Gaussian {
 #pragma unroll
     for (int k = 0; k < N; ++k)
       d[k] = x[k] - beta;
-    PGN_GENZ_SQUARES(N, d, sq);
+    ::pagani_b200::fastmath::pow2_pinned_n<N>(d, sq);
     double s = pow(25., 2.) * sq[0];
 #pragma unroll
     for (int k = 1; k < N; ++k)
