@@ -83,6 +83,18 @@ class pgn_rule_view(C.Structure):
     ]
 
 
+class pgn_heuristic_result(C.Structure):
+    _fields_ = [
+        ("success", C.c_int32),
+        ("must_terminate", C.c_int32),
+        ("probes", C.c_int32),
+        ("reserved", C.c_int32),
+        ("num_active", C.c_uint64),
+        ("threshold", C.c_double),
+        ("finished_errorest", C.c_double),
+    ]
+
+
 class pgn_iter_stats(C.Structure):
     _fields_ = [
         ("iteration", C.c_uint64),
@@ -167,6 +179,8 @@ SIGNATURES = {
     "pgn_classify": (C.c_int, [_vp, C.c_double, C.c_int, _P(pgn_iter_stats)]),
     "pgn_set_active": (C.c_int, [_vp, _P(C.c_uint8), C.c_size_t]),
     "pgn_set_estimates": (C.c_int, [_vp, _dp, _dp, _P(C.c_int32), C.c_size_t]),
+    "pgn_heuristic_classify": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                         _P(pgn_heuristic_result)]),
     "pgn_filter": (C.c_int, [_vp, _P(C.c_size_t)]),
     "pgn_split": (C.c_int, [_vp]),
     "pgn_fetch_estimates": (C.c_int, [_vp, _dp, _dp, _P(C.c_int32), _P(C.c_uint8), C.c_size_t]),

@@ -246,6 +246,15 @@ pgn_filter(pgn_ctx* ctx, size_t* num_active)
 }
 
 int
+pgn_heuristic_classify(pgn_ctx* ctx, double epsrel, double last_estimate, double iter_errorest,
+                       double iter_finished_errorest, double total_finished_errorest, pgn_heuristic_result* out)
+{
+  return ctx ? ctx->engine.heuristic_classify_stage(epsrel, last_estimate, iter_errorest, iter_finished_errorest,
+                                                    total_finished_errorest, out)
+             : PGN_ERR_INVALID;
+}
+
+int
 pgn_split(pgn_ctx* ctx)
 {
   return ctx ? ctx->engine.split() : PGN_ERR_INVALID;

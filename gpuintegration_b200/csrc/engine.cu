@@ -769,6 +769,34 @@ Engine::classify(double epsrel, int relerr, pgn_iter_stats* out)
   return PGN_OK;
 }
 
+// Stage-level Heuristic_classifier::classify on the current error list (pgn_heuristic_classify).
+int
+Engine::heuristic_classify_stage(double epsrel, double last_estimate, double iter_errorest,
+                                 double iter_finished_errorest, double total_finished_errorest,
+                                 pgn_heuristic_result* out)
+{
+  if (!out)
+    return PGN_ERR_INVALID;
+  PGN_CUDA(cudaSetDevice(device_));
+  if (!classified_ || n_ == 0) {
+    set_last_error("heuristic_classify() needs a classified, non-empty region list");
+    return PGN_ERR_STATE;
+  }
+  tracker_.reset(epsrel, 0.0);
+  for (int k = 0; k < 3; ++k)
+    tracker_.store(last_estimate);
+  HeuristicOutcome hs;
+  PGN_TRY(heuristic_classify(n_, 0.0, iter_errorest, iter_finished_errorest, total_finished_errorest, &hs, true));
+  std::memset(out, 0, sizeof *out);
+  out->success = hs.success ? 1 : 0;
+  out->must_terminate = hs.must_terminate ? 1 : 0;
+  out->probes = hs.probes;
+  out->num_active = hs.num_active;
+  out->threshold = hs.threshold;
+  out->finished_errorest = hs.finished_errorest;
+  return PGN_OK;
+}
+
 int
 Engine::set_active(const uint8_t* flags, size_t n)
 {
@@ -1150,7 +1178,7 @@ Engine::mem_capacity_bytes() const
 
 int
 Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, double fin_err,
-                           double cum_err, HeuristicOutcome* out)
+                           double cum_err, HeuristicOutcome* out, bool force)
 {
   (void)iter_est;
   // heuristic_classifier.cuh:105-145, 227-264: bytes a full split of n regions would need
@@ -1163,7 +1191,7 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
   const double ratio = static_cast<double>(required) / static_cast<double>(free_mem);
   const bool necessary = ratio > 1.;
   const bool criteria = ratio > 1. || (ratio > .1 && tracker_.converged());
-  if (!criteria) {
+  if (!criteria && !force) {
     out->must_terminate = necessary;
     return PGN_OK;
   }

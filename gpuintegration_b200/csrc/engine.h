@@ -69,6 +69,9 @@ public:
   int set_active(const uint8_t* flags, size_t n);
   int set_estimates(const double* est, const double* err, const int32_t* axis, size_t n);
   int filter(size_t* num_active);
+  int heuristic_classify_stage(double epsrel, double last_estimate, double iter_errorest,
+                               double iter_finished_errorest, double total_finished_errorest,
+                               pgn_heuristic_result* out);
   int split();
   int fetch_estimates(double* est, double* err, int32_t* axis, uint8_t* active, size_t cap);
   int fetch_parents(double* est, double* err, int32_t* axis, size_t cap, size_t* n);
@@ -116,7 +119,7 @@ private:
     int probes = 0;
   };
   int heuristic_classify(size_t n_global, double iter_est, double iter_err, double fin_err,
-                         double cum_err, HeuristicOutcome* out);
+                         double cum_err, HeuristicOutcome* out, bool force = false);
   // bucket partition of the current errors for the device-side threshold search
   int prepare_search(const struct BucketPlan& plan, struct BucketTables* tables);
   double mem_capacity_bytes() const;

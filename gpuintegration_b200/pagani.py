@@ -262,6 +262,17 @@ class Workspace:
             "pgn_set_estimates",
         )
 
+    def heuristic_classify(self, epsrel, last_estimate, iter_errorest, iter_finished_errorest=0.0,
+                           total_finished_errorest=0.0):
+        """Heuristic_classifier::classify (heuristic_classifier.cuh:362-451) on the current error list, as the
+        reference's classifier test drives it; needs classify() or set_active() first."""
+        r = capi.pgn_heuristic_result()
+        capi.check(self._lib.pgn_heuristic_classify(self._ctx, epsrel, last_estimate, iter_errorest,
+                                                    iter_finished_errorest, total_finished_errorest, C.byref(r)),
+                   "pgn_heuristic_classify")
+        return {"success": bool(r.success), "must_terminate": bool(r.must_terminate), "probes": r.probes,
+                "num_active": r.num_active, "threshold": r.threshold, "finished_errorest": r.finished_errorest}
+
     def filter(self):
         m = C.c_size_t()
         capi.check(self._lib.pgn_filter(self._ctx, C.byref(m)), "pgn_filter")

@@ -173,6 +173,22 @@ int pgn_set_estimates(pgn_ctx* ctx, const double* estimate, const double* errore
 int pgn_filter(pgn_ctx* ctx, size_t* num_active);
 /* Sub_region_splitter::split (Sub_region_splitter.cuh:55-87). */
 int pgn_split(pgn_ctx* ctx);
+/* Heuristic_classifier::classify (heuristic_classifier.cuh:362-451) on the CURRENT error list, regardless of the
+ * memory-pressure criteria (the reference's classifier test drives it directly,
+ * test/kokkos/pagani/test_heuristic_classifier.cpp:32-103).  Needs pgn_classify / pgn_set_active first (statistics).
+ * last_estimate is what Heuristic_classifier::store_estimate saw last; on success the active flags are replaced by
+ * the ones the search adopted (those of its last probe). */
+typedef struct pgn_heuristic_result {
+  int32_t success;        /* pass_mem && pass_errorest_budget */
+  int32_t must_terminate; /* Workspace::heuristic_classify's return value had the criteria been met */
+  int32_t probes;
+  int32_t reserved;
+  uint64_t num_active;
+  double threshold;        /* of the last probe */
+  double finished_errorest;
+} pgn_heuristic_result;
+int pgn_heuristic_classify(pgn_ctx* ctx, double epsrel, double last_estimate, double iter_errorest,
+                           double iter_finished_errorest, double total_finished_errorest, pgn_heuristic_result* out);
 /* copies of the per-region arrays of the current iteration (any pointer may be NULL) */
 int pgn_fetch_estimates(pgn_ctx* ctx, double* estimate, double* errorest, int32_t* axis, uint8_t* active, size_t cap);
 int pgn_fetch_parents(pgn_ctx* ctx, double* estimate, double* errorest, int32_t* axis, size_t cap, size_t* n);
