@@ -8,7 +8,9 @@
 //
 // Pinning: tests/test_oracle_golden.py checks this file against per-iteration trajectories recorded
 // from the reference binary on a B200 (tests/golden/trajectories/*.json, made by
-// tools/make_golden_trajectories.py) and against the reference tests' known answers.
+// tools/make_golden_trajectories.py) and against the reference tests' known answers, among them the
+// heuristic classifier's own (test/kokkos/pagani/test_heuristic_classifier.cpp:32-103) through
+// orc_classify_threshold.
 // Host libm (cos/exp/pow) is not bit-identical to CUDA's libdevice, so per-region values agree to
 // ~1e-15 relative rather than bit-for-bit; the golden comparison states its tolerances.
 #include <algorithm>
