@@ -26,7 +26,8 @@ pytestmark = pytest.mark.skipif(not oracle.available(), reason="oracle/libpagani
 # with axis 3), and then the last bit of f(x) picks the split axis.  Host libm does not reproduce
 # CUDA libdevice to the last bit, so the oracle is compared exactly up to and including the first
 # iteration whose split axes differ; the cases below are known to stay exact to the end.
-FULLY_EXACT = {"f6_6_0.001", "const_2_0.001", "xy_2_1e-06"}
+# (x*y is bilinear: its fourth differences are pure rounding noise, which the host does not reproduce)
+FULLY_EXACT = {"f6_6_0.001", "const_2_0.001"}
 
 
 def leading_iterations(doc, feval):
@@ -47,7 +48,7 @@ def test_oracle_follows_reference_trajectory(path):
     family = {0: 0, 7: -1}.get(fam, fam)
     t = oracle.Tables(nd)
     k = leading_iterations(doc, t.feval)
-    assert k >= 2, "fixture too heavy for the CPU oracle"
+    assert k >= min(2, len(doc["iterations"])), "fixture too heavy for the CPU oracle"
     res, its = oracle.integrate(family, nd, doc["epsrel"], doc["epsabs"], max_iters=k)
     ref = doc["iterations"][:k]
     assert len(its) == len(ref)

@@ -20,10 +20,14 @@ import refharness  # noqa: E402
 
 # (family, ndim, epsrel, keep raw arrays of iterations with <= this many regions)
 CASES = [
-    (1, 8, 1e-3, 2048), (1, 8, 1e-5, 0), (1, 8, 1e-6, 0), (4, 5, 1e-3, 1024), (4, 8, 1e-4, 0), (5, 8, 1e-3, 1024),
-    (6, 6, 1e-3, 4096), (2, 6, 1e-3, 512), (2, 6, 1e-5, 0), (3, 8, 1e-3, 4096), (5, 10, 1e-3, 2048),
-    (6, 10, 1e-3, 2048), (1, 5, 1e-6, 512), (3, 5, 1e-5, 512), (4, 7, 1e-4, 0), (6, 7, 1e-3, 512),
-    (0, 2, 1e-3, 4096), (7, 2, 1e-6, 4096),
+    # BASELINE configs[1]: F_1_8D at all six tolerances of the bench step
+    (1, 8, 1e-3, 1024), (1, 8, 1e-4, 0), (1, 8, 1e-5, 0), (1, 8, 1e-6, 0), (1, 8, 1e-7, 0), (1, 8, 1e-8, 0),
+    # configs[0] integrand, configs[2] (F_2_6D 1e-7), configs[3] (10-D C0 / discontinuous), configs[4] (F_4_8D 1e-9)
+    (4, 5, 1e-3, 1024), (2, 6, 1e-7, 0), (5, 10, 1e-3, 1024), (5, 10, 1e-4, 0), (6, 10, 1e-3, 1024), (6, 10, 1e-4, 0),
+    (4, 8, 1e-9, 0),
+    # the other families / dimensions
+    (4, 8, 1e-4, 0), (5, 8, 1e-3, 1024), (6, 6, 1e-3, 1024), (2, 6, 1e-3, 512), (2, 6, 1e-5, 0), (3, 8, 1e-3, 1024),
+    (1, 5, 1e-6, 512), (3, 5, 1e-5, 512), (4, 7, 1e-4, 0), (6, 7, 1e-3, 512), (0, 2, 1e-3, 1024), (7, 2, 1e-6, 1024),
 ]
 NAMES = {0: "const", 7: "xy"}
 
