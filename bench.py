@@ -88,7 +88,8 @@ def run_reference(args, rank):
     evals = seconds = 0.0
     last = None
     for i in range(args.warmup + args.steps):
-        r = oracle_cpu.cuhre(FAMILY, NDIM, EPSRELS[0], epsabs=1e-100, maxeval=10**11, threads=0, time_cap_s=cap)
+        # threads given explicitly: under torchrun OMP_NUM_THREADS is 1, and "all threads" (0) would mean one
+        r = oracle_cpu.cuhre(FAMILY, NDIM, EPSRELS[0], epsabs=1e-100, maxeval=10**11, threads=cores, time_cap_s=cap)
         if i >= args.warmup:
             evals += r["neval"]
             seconds += r["seconds"]
@@ -109,6 +110,176 @@ def run_reference(args, rank):
     }))
 
 
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden", "trajectories")
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "ncu_eval_f1_8d.json")
+
+
+def load_ncu_summary():
+    """Figures of the committed `ncu --set full` capture of the evaluation kernel (written by tools/ncu_summary.py
+    from the .ncu-rep): FP64 pipe utilisation, executed FP64 flops per evaluation, DRAM bytes per region."""
+    try:
+        return json.load(open(NCU_SUMMARY))
+    except (OSError, ValueError):
+        return None
+
+
+
+def golden_tag(family, ndim, eps):
+    return f"f{family}_{ndim}_{eps:g}"
+
+
+def check_against_golden(family, ndim, eps, res, trace):
+    """Compare one integrate() call with the trajectory the UNMODIFIED reference produced on a B200 for the same
+    integrand and tolerance (tests/golden/trajectories, recorded by tools/make_golden_trajectories.py from
+    oracle/_ref/ref_pagani): per-iteration global region count, surviving regions, heuristic-filter decisions,
+    budget-overflow decisions, and the summary.  Works at any rank count (the quantities are global)."""
+    path = os.path.join(GOLDEN_DIR, golden_tag(family, ndim, eps) + ".json")
+    if not os.path.exists(path):
+        return {"case": golden_tag(family, ndim, eps), "ok": None, "why": "no golden fixture"}
+    doc = json.load(open(path))
+    bad = []
+    its, s = doc["iterations"], doc["summary"]
+    if len(trace) != len(its):
+        bad.append(f"iterations {len(trace)} != {len(its)}")
+    for r, m in zip(its, trace):
+        if m["nregions_global"] != r["n"]:
+            bad.append(f"it {r['it']}: regions {m['nregions_global']} != {r['n']}")
+        if m["heuristic_ran"] != r["heuristic_ran"]:
+            bad.append(f"it {r['it']}: heuristic_ran {m['heuristic_ran']} != {r['heuristic_ran']}")
+        if m["budget_overflow"] != r["budget_overflow"]:
+            bad.append(f"it {r['it']}: budget_overflow {m['budget_overflow']} != {r['budget_overflow']}")
+        if r["outcome"] == "split" and m["nactive"] != r["nactive"]:
+            bad.append(f"it {r['it']}: active {m['nactive']} != {r['nactive']}")
+        scale = max(abs(r["iter_estimate"]), r["iter_errorest"])
+        if abs(m["iter_estimate"] - r["iter_estimate"]) > 1e-12 * scale:
+            bad.append(f"it {r['it']}: iteration estimate differs by more than 1e-12")
+    if (res.status, res.nregions, res.iters) != (s["status"], s["nregions"], s["iters"]):
+        bad.append(f"summary (status, nregions, iters) {(res.status, res.nregions, res.iters)} != "
+                   f"{(s['status'], s['nregions'], s['iters'])}")
+    if abs(res.estimate - s["estimate"]) > 1e-12 * max(abs(s["estimate"]), s["errorest"]):
+        bad.append("final estimate differs by more than 1e-12")
+    return {"case": golden_tag(family, ndim, eps), "ok": not bad, "iterations": len(its), "mismatches": bad[:5]}
+
+
+def timed_integrate(ws, g, eps, repeats=2):
+    """min wall ms over `repeats` calls of ws.integrate (collective under torchrun) -> (ms, result, trace)."""
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        r = ws.integrate(g, eps, EPSABS)
+        dt = (time.perf_counter() - t0) * 1e3
+        best = dt if best is None or dt < best else best
+    return best, r, ws.trace()
+
+
+def reference_gpu_ms(name, eps, repeats=4):
+    """Unmodified reference CUDA PAGANI on this GPU: min wall ms of Workspace::integrate over the repeats after the
+    first (the reference's own protocol discards the first run, new_time_and_call.cuh:230-238)."""
+    import refharness
+
+    if not refharness.available():
+        return None
+    lines = refharness.integrate(name, eps, EPSABS, repeats=repeats)
+    runs = [l for l in lines if "ms" in l]
+    keep = runs[1:] if len(runs) > 1 else runs
+    best = min(keep, key=lambda l: l["ms"])
+    return {"ms": best["ms"], "ms_all": [l["ms"] for l in runs], "status": best["status"], "nregions": best["nregions"],
+            "estimate": best.get("estimate"), "errorest": best.get("errorest")}
+
+
+def cpu_cuhre(family, ndim, eps, cap_s, cores):
+    import oracle_cpu
+
+    c = oracle_cpu.cuhre(family, ndim, eps, epsabs=1e-100, maxeval=10**11, threads=cores, time_cap_s=cap_s)
+    return {"seconds": c["seconds"], "status": c["status"], "neval": c["neval"], "threads": c["threads"],
+            "evals_per_s": c["neval"] / c["seconds"] if c["seconds"] > 0 else None,
+            "reached_relerr": c["errorest"] / abs(c["estimate"]) if c["estimate"] else None, "cap_s": cap_s,
+            "label": "Cuhre (restated, not libcuba)"}
+
+
+# BASELINE.json configs[2..4] as side records: (label, family, ndim, epsrel)
+SIDE_CONFIGS = [
+    ("config3 F_2_6D product peak, epsrel 1e-7", 2, 6, 1e-7),
+    ("config4a F_5_10D C0, epsrel 1e-3", 5, 10, 1e-3),
+    ("config4b F_6_10D discontinuous (SURVEY 8d parameters), epsrel 1e-3", 6, 10, 1e-3),
+    ("config5 F_4_8D Gaussian, epsrel 1e-9", 4, 8, 1e-9),
+]
+
+
+def run_side_configs(pg, parallel, local_rank, world):
+    """configs[2..4] in the reference's memory model, trajectory checked against the golden.  Collective: every rank
+    calls it (add_side_baselines adds the reference kernels and CPU Cuhre on rank 0 afterwards)."""
+    out = []
+    for label, family, ndim, eps in SIDE_CONFIGS:
+        ws = pg.Workspace(ndim, device=local_rank, mem_mode="parity", trace=True)
+        if world > 1:
+            parallel.attach_nccl(ws)
+        g = pg.Genz(family, ndim)
+        ms, r, tr = timed_integrate(ws, g, eps)
+        ms = parallel.max_over_ranks(ms)
+        ws.close()
+        rec = {"config": label, "family": family, "ndim": ndim, "epsrel": eps, "n_gpus": world,
+               "ours": {"ms": ms, "status": r.status, "estimate": r.estimate, "errorest": r.errorest, "nregions": r.nregions,
+                        "iters": r.iters, "neval": r.neval, "evals_per_s": r.neval / (ms * 1e-3),
+                        "max_regions_in_flight": max(t["nregions_global"] for t in tr),
+                        "heuristic_iterations": sum(1 for t in tr if t["heuristic_ran"]),
+                        "true_value": g.true_value, "rel_err_vs_true": abs(r.estimate - g.true_value) / abs(g.true_value)},
+               "parity": check_against_golden(family, ndim, eps, r, tr)}
+        out.append(rec)
+    return out
+
+
+def add_side_baselines(records, cores):
+    """Rank 0 only, after every collective leg: the reference kernels on this GPU and CPU Cuhre at the same tolerance."""
+    for rec in records:
+        family, ndim, eps = rec["family"], rec["ndim"], rec["epsrel"]
+        try:
+            ref = reference_gpu_ms(f"f{family}_{ndim}", eps)
+            if ref:
+                rec["reference_gpu"] = ref
+                rec["speedup_vs_reference_gpu"] = ref["ms"] / rec["ours"]["ms"]
+                rec["reference_gpu"]["same_nregions_as_ours"] = ref["nregions"] == rec["ours"]["nregions"]
+        except Exception as e:  # noqa: BLE001
+            rec["reference_gpu"] = {"error": repr(e)}
+        try:
+            rec["cpu_cuhre_same_epsrel"] = cpu_cuhre(family, ndim, eps, 6.0, cores)
+        except Exception as e:  # noqa: BLE001
+            rec["cpu_cuhre_same_epsrel"] = {"error": repr(e)}
+
+
+def run_native_ladder(pg, parallel, local_rank, world, budget_s):
+    """The reference's tolerance ladder (new_interface_Genz1_8D.cu:9-25: epsrel divided by 5 until the first run
+    that does not converge) on F_1_8D with the NATIVE memory model (free HBM of all ranks instead of the reference's
+    hard-wired 16e9 bytes), so that tight tolerances are actually reached.  Stops at the first failure or when the
+    wall-time budget is used up.  Collective."""
+    ws = pg.Workspace(NDIM, device=local_rank, mem_mode="native", trace=True)
+    if world > 1:
+        parallel.attach_nccl(ws)
+    g = pg.Genz(FAMILY, NDIM)
+    steps, eps, t_start, stopped = [], 1e-3, time.perf_counter(), "first failure"
+    while eps > 1e-12:
+        t0 = time.perf_counter()
+        r = ws.integrate(g, eps, EPSABS)
+        ms = parallel.max_over_ranks((time.perf_counter() - t0) * 1e3)
+        tr = ws.trace()
+        steps.append({"epsrel": eps, "status": r.status, "time_to_epsrel_ms": ms if r.status == 0 else None, "ms": ms,
+                      "estimate": r.estimate, "errorest": r.errorest, "nregions": r.nregions, "iters": r.iters,
+                      "neval": r.neval, "evals_per_s": r.neval / (ms * 1e-3),
+                      "rel_err_vs_true": abs(r.estimate - g.true_value) / abs(g.true_value),
+                      "max_regions_in_flight": max(t["nregions_global"] for t in tr)})
+        if r.status != 0:
+            break
+        # every rank must take the same decision: the slowest rank's clock decides
+        if parallel.max_over_ranks(time.perf_counter() - t_start) > budget_s:
+            stopped = f"wall-time budget of {budget_s:g} s"
+            break
+        eps /= 5.0
+    ws.close()
+    reached = [s["epsrel"] for s in steps if s["status"] == 0]
+    return {"integrand": "F_1_8D", "mem_mode": "native", "n_gpus": world, "stopped_by": stopped,
+            "tightest_epsrel_reached": min(reached) if reached else None, "steps": steps}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -116,7 +287,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mem-mode", default="parity", choices=["parity", "native"])
-    ap.add_argument("--no-side-legs", action="store_true", help="skip cpu_baseline / reference-GPU legs")
+    ap.add_argument("--no-side-legs", action="store_true", help="skip cpu_baseline / reference-GPU / configs / ladder legs")
+    ap.add_argument("--ladder-budget-s", type=float, default=45.0, help="wall-time budget of the native-mode tolerance ladder")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -202,12 +374,10 @@ def main():
     e2e_evals = 0
     for _ in range(args.steps):
         for eps in EPSRELS:
-            if world == 1:
-                ws.import_regions(pin_left.numpy(), pin_len.numpy())
-                r = ws.integrate(g, eps, EPSABS, subregions=True)
-                h2d += 2 * pin_left.numel() * 8
-            else:
-                r = ws.integrate(g, eps, EPSABS)
+            # every rank uploads its slice of the initial region list from pinned host memory
+            ws.import_regions(pin_left.numpy(), pin_len.numpy())
+            r = ws.integrate(g, eps, EPSABS, subregions=True)
+            h2d += 2 * pin_left.numel() * 8 * world
             tr = ws.trace()
             d2h += 64 + 256 * (len(tr) + sum(t["heuristic_probes"] for t in tr))
             e2e_evals += r.neval
@@ -215,8 +385,21 @@ def main():
     e2e_wall = parallel.max_over_ranks(time.perf_counter() - t0)
     e2e_value = e2e_evals / e2e_wall
 
+    # ---- trajectory parity of the timed calls against the reference's goldens (global quantities: any rank count)
+    parity = [check_against_golden(FAMILY, NDIM, eps, r, tr) for eps, r, tr in collected[:len(EPSRELS)]]
+    if args.mem_mode != "parity":
+        parity = []
+    parity_ok = bool(parity) and all(p["ok"] for p in parity)
+    ws.close()
+
+    # ---- collective side legs (every rank takes part, rank 0 reports)
+    cores = os.cpu_count() or 1
+    side_configs = ladder = None
+    if not args.no_side_legs:
+        side_configs = run_side_configs(pg, parallel, local_rank, world)
+        ladder = run_native_ladder(pg, parallel, local_rank, world, args.ladder_budget_s)
+
     if rank != 0:
-        ws.close()
         if world > 1:
             torch.distributed.barrier()
             torch.distributed.destroy_process_group()
@@ -255,16 +438,17 @@ def main():
                 "d2h_bytes_per_step": d2h // args.steps, "wall_ms_per_step": 1e3 * e2e_wall / args.steps,
                 "path": "gpuintegration_b200.Workspace.integrate (ctypes -> C ABI pgn_integrate), initial region "
                         "list uploaded from pinned host memory, integration_result + per-iteration statistics "
-                        "read back" if world == 1 else "gpuintegration_b200.Workspace.integrate on every rank"},
+                        "read back (every rank uploads its slice; bytes are summed over the ranks)"},
         "gpu_launches": launches,
+        "parity_ok": parity_ok if parity else None,
+        "parity": {"against": "tests/golden/trajectories (unmodified reference PAGANI on a B200, oracle/_ref/ref_pagani)",
+                   "checked": "per iteration: global regions, surviving regions, heuristic / budget-overflow decisions, "
+                              "iteration estimate <= 1e-12; summary: status, nregions, iters, estimate <= 1e-12",
+                   "cases": parity},
         "wall_ms_per_step_timed_region": 1e3 * wall / args.steps,
         "roofline": {"bound": "fp64", "kernel": "pagani_b200::detail::evaluate_kernel_bp<Oscillatory<8>>",
                      "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
-                     # DRAM bytes per launch: 128.9 B per region (ncu, below) x regions of the average launch
-                     "traffic": 128.9 * (local_evals / feval) / max(n_eval_launches, 1),
-                     "traffic_note": "ncu --set full, 65536-region launch (profiles/r01_ncu_eval_s8_final.txt): 8.45 MB read, "
-                                     "0 B written back before the kernel ends = 129 B per region for 16*ndim+20 = 148 "
-                                     "algorithmic bytes (part of the bounds is still in L2 from the split kernel)",
+                     "traffic": None,
                      "note": "ALGORITHMIC flops (SURVEY 8d: 107 per F_1_8D evaluation x 1105 evaluations per region) "
                              "over the CUDA-event time of the evaluation launches of rank 0; peak = FP64 FMA "
                              "micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure); "
@@ -278,6 +462,25 @@ def main():
         "hbm_peak_gbs": peaks.get("hbm_gbs"),
     }
 
+    if side_configs is not None:
+        add_side_baselines(side_configs, cores)
+        out["configs"] = side_configs
+        out["native_ladder"] = ladder
+    ncu = load_ncu_summary()
+    if ncu:
+        # executed (not contract) FP64 work and the pipe utilisation, from the committed ncu capture of this kernel
+        out["roofline"]["fp64_pipe_pct"] = ncu.get("fp64_pipe_pct")
+        out["roofline"]["fp64_flops_executed_per_eval"] = ncu.get("fp64_flops_executed_per_eval")
+        if ncu.get("fp64_flops_executed_per_eval"):
+            out["roofline"]["frac_executed"] = (local_evals * ncu["fp64_flops_executed_per_eval"] / (eval_ms * 1e-3) / 1e12
+                                                / fp64_peak)
+        if ncu.get("dram_bytes_per_region"):
+            out["roofline"]["traffic"] = ncu["dram_bytes_per_region"] * (local_evals / feval) / max(n_eval_launches, 1)
+            out["roofline"]["traffic_note"] = (
+                f"dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture ({ncu.get('source')}: "
+                f"{ncu.get('regions')} regions, {ncu['dram_bytes_per_region']:.1f} B per region for 16*ndim+20 = "
+                f"{16 * NDIM + 20} algorithmic bytes) x regions of the average launch of this run")
+        out["roofline"]["ncu_source"] = ncu.get("source")
     if not args.no_side_legs and world == 1:
         # HBM-bound stages at the largest iteration: classify 29 B/region, fused compact+split (48 ndim + 36) B
         # per surviving region, measured peak from MEASURED_PEAKS.json (driver-written copy bandwidth)
@@ -311,9 +514,10 @@ def main():
         try:
             import oracle_cpu
 
-            c = oracle_cpu.cuhre(FAMILY, NDIM, EPSRELS[0], epsabs=1e-100, maxeval=10**11, threads=0, time_cap_s=12.0)
+            c = oracle_cpu.cuhre(FAMILY, NDIM, EPSRELS[0], epsabs=1e-100, maxeval=10**11, threads=cores, time_cap_s=12.0)
             out["cpu_baseline"] = {
                 "value": c["neval"] / c["seconds"], "unit": "evals/s", "cores": c["threads"], "kind": "port",
+                "host_cores_available": cores,
                 "sample": f"Cuhre (restated, not libcuba) on F_1_8D at epsrel 1e-3, capped at 12 s "
                           f"(status {c['status']}, reached relative error estimate {c['errorest'] / abs(c['estimate']):.2e} "
                           f"after {c['neval']} evaluations)"}
@@ -326,17 +530,17 @@ def main():
             if refharness.available():
                 ref = []
                 for (eps, r, _tr) in first:
-                    lines = refharness.integrate(refharness.genz_name(FAMILY, NDIM), eps, EPSABS, repeats=2)
-                    ref.append({"epsrel": eps, "ms": lines[-1]["ms"], "status": lines[-1]["status"],
-                                "nregions": lines[-1]["nregions"], "same_nregions_as_ours": lines[-1]["nregions"] == r.nregions})
+                    x = reference_gpu_ms(refharness.genz_name(FAMILY, NDIM), eps, repeats=4)
+                    ref.append({"epsrel": eps, "ms": x["ms"], "ms_all": x["ms_all"], "status": x["status"],
+                                "nregions": x["nregions"], "same_nregions_as_ours": x["nregions"] == r.nregions})
                 ref_s = sum(x["ms"] for x in ref) * 1e-3
                 out["reference_gpu"] = {"what": "unmodified reference CUDA PAGANI (oracle/_ref/ref_pagani, sm_100a build) "
-                                                "on the same GPU, wall ms of Workspace::integrate per epsrel, 2nd repeat",
+                                                "on the same GPU, wall ms of Workspace::integrate per epsrel: minimum of "
+                                                "repeats 2..4 (the first is discarded, as new_time_and_call.cuh does)",
                                         "evals_per_s": evals_per_step / ref_s, "ms_per_step": 1e3 * ref_s, "per_epsrel": ref,
                                         "speedup_e2e": e2e_value / (evals_per_step / ref_s)}
         except Exception as e:  # noqa: BLE001
             out["reference_gpu"] = {"error": repr(e)}
-    ws.close()
     print(json.dumps(out), flush=True)
     if world > 1:
         torch.distributed.barrier()

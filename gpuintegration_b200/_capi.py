@@ -197,6 +197,13 @@ SIGNATURES = {
     "pgn_nccl_unique_id": (C.c_int, [_P(C.c_uint8)]),
     "pgn_comm_init": (C.c_int, [_vp, _P(C.c_uint8), C.c_int, C.c_int]),
     "pgn_comm_size": (C.c_int, [_vp, _P(C.c_int), _P(C.c_int)]),
+    "pgn_dev_uniform_split": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_size_t]),
+    "pgn_dev_evaluate": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp, _dp, _dp]),
+    "pgn_dev_count_active": (C.c_int, [_vp, _vp, C.c_size_t, _P(C.c_size_t)]),
+    "pgn_dev_filter": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, C.c_size_t, _vp, _vp, _vp, _vp, _vp]),
+    "pgn_dev_split": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t, _vp, _vp]),
+    "pgn_regions_import_device": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "pgn_regions_export_device": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _P(C.c_size_t)]),
     "pgn_set_rebalance": (C.c_int, [_vp, C.c_double, C.c_size_t]),
     "pgn_comm_set_host_collective": (C.c_int, [_vp, C.c_int, C.c_int, pgn_allreduce_fn, pgn_alltoallv_fn, _vp]),
     "pgn_plan_rebalance": (C.c_int, [_P(C.c_uint64), C.c_int, _P(C.c_uint64), _P(C.c_uint64), C.c_int, _P(C.c_int)]),

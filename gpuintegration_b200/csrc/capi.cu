@@ -47,6 +47,7 @@ const GenzEntry kGenz[] = {
   // the reference unit tests' integrands: family 0 constant, 7 product of coordinates, 8 NaN
   entry<testfn::Constant<2>>(0),    entry<testfn::Constant<3>>(0),    entry<testfn::Constant<5>>(0),
   entry<testfn::Constant<8>>(0),    entry<testfn::Product<2>>(7),     entry<testfn::NotANumber<2>>(8),
+  entry<testfn::Product<3>>(7),     entry<testfn::Product<4>>(7),
 };
 
 const GenzEntry*
@@ -258,6 +259,57 @@ int
 pgn_split(pgn_ctx* ctx)
 {
   return ctx ? ctx->engine.split() : PGN_ERR_INVALID;
+}
+
+int
+pgn_dev_uniform_split(pgn_ctx* ctx, int parts_per_axis, double* d_left, double* d_length, size_t n)
+{
+  return ctx ? ctx->engine.dev_uniform_split(parts_per_axis, d_left, d_length, n) : PGN_ERR_INVALID;
+}
+
+int
+pgn_dev_evaluate(pgn_ctx* ctx, pgn_eval_fn fn, void* user, const double* d_left, const double* d_length, size_t n,
+                 double* d_estimate, double* d_errorest, int32_t* d_axis, double* d_active, double* sum_estimate,
+                 double* sum_errorest)
+{
+  return ctx ? ctx->engine.dev_evaluate(fn, user, d_left, d_length, n, d_estimate, d_errorest, d_axis, d_active,
+                                        sum_estimate, sum_errorest)
+             : PGN_ERR_INVALID;
+}
+
+int
+pgn_dev_count_active(pgn_ctx* ctx, const double* d_active, size_t n, size_t* count)
+{
+  return ctx ? ctx->engine.dev_count_active(d_active, n, count) : PGN_ERR_INVALID;
+}
+
+int
+pgn_dev_filter(pgn_ctx* ctx, const double* d_left, const double* d_length, const double* d_estimate,
+               const double* d_errorest, const int32_t* d_axis, const double* d_active, size_t n, size_t m,
+               double* out_left, double* out_length, double* out_estimate, double* out_errorest, int32_t* out_axis)
+{
+  return ctx ? ctx->engine.dev_filter(d_left, d_length, d_estimate, d_errorest, d_axis, d_active, n, m, out_left,
+                                      out_length, out_estimate, out_errorest, out_axis)
+             : PGN_ERR_INVALID;
+}
+
+int
+pgn_dev_split(pgn_ctx* ctx, const double* d_left, const double* d_length, const int32_t* d_axis, size_t m,
+              double* out_left, double* out_length)
+{
+  return ctx ? ctx->engine.dev_split(d_left, d_length, d_axis, m, out_left, out_length) : PGN_ERR_INVALID;
+}
+
+int
+pgn_regions_import_device(pgn_ctx* ctx, const double* d_left, const double* d_length, size_t n)
+{
+  return ctx ? ctx->engine.regions_import_device(d_left, d_length, n) : PGN_ERR_INVALID;
+}
+
+int
+pgn_regions_export_device(pgn_ctx* ctx, double* d_left, double* d_length, size_t cap, size_t* n)
+{
+  return ctx ? ctx->engine.regions_export_device(d_left, d_length, cap, n) : PGN_ERR_INVALID;
 }
 
 int

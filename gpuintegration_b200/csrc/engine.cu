@@ -237,9 +237,8 @@ Engine::~Engine()
     cudaFreeHost(host_global_);
   if (host_search_)
     cudaFreeHost(host_search_);
-  for (cudaEvent_t& e : ev_)
-    if (e)
-      cudaEventDestroy(e);
+  for (cudaEvent_t e : ev_pool_)
+    cudaEventDestroy(e);
   if (stream_)
     cudaStreamDestroy(stream_);
 }
@@ -275,8 +274,6 @@ Engine::init()
   }
   sm_count_ = prop.multiProcessorCount;
   PGN_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-  for (cudaEvent_t& e : ev_)
-    PGN_CUDA(cudaEventCreate(&e));
 
   PGN_TRY(d_codes_.reserve(sizeof(uint64_t) * rule_.feval));
   PGN_TRY(d_weights_.reserve(sizeof(double) * kSets * kRules));
@@ -486,16 +483,24 @@ Engine::launch_evaluate(pgn_eval_fn fn, void* user)
   PGN_TRY(ensure_iteration_buffers(n_));
   if (n_ == 0)
     return PGN_OK;
+  return launch_evaluate_on(fn, user, left_[cur_].as<double>(), length_[cur_].as<double>(), n_, est_.as<double>(),
+                            err_raw_.as<double>(), axis_.as<int32_t>());
+}
+
+int
+Engine::launch_evaluate_on(pgn_eval_fn fn, void* user, const double* left, const double* length, size_t n,
+                           double* est, double* err, int32_t* axis)
+{
   pgn_region_view v;
   std::memset(&v, 0, sizeof v);
   v.abi_version = PGN_ABI_VERSION;
   v.view_bytes = static_cast<uint32_t>(sizeof v);
-  v.left = left_[cur_].as<double>();
-  v.length = length_[cur_].as<double>();
-  v.n = n_;
-  v.estimate = est_.as<double>();
-  v.errorest = err_raw_.as<double>();
-  v.axis = axis_.as<int32_t>();
+  v.left = left;
+  v.length = length;
+  v.n = n;
+  v.estimate = est;
+  v.errorest = err;
+  v.axis = axis;
   for (int d = 0; d <= PGN_MAX_NDIM; ++d) {
     v.lows[d] = lows_[d];
     v.ranges[d] = ranges_[d];
@@ -589,7 +594,7 @@ Engine::fill_peer_box(PeerBox* box, long long spin_limit) const
 // statistics itself; every rank launches the same sequence of statistics kernels, so the exchange
 // numbers agree.
 TileScratch
-Engine::make_scratch()
+Engine::make_scratch(bool allow_fused)
 {
   TileScratch ts;
   std::memset(&ts, 0, sizeof ts);
@@ -602,7 +607,7 @@ Engine::make_scratch()
   ts.nranks = comm_ ? comm_->nranks : 1;
   ts.stats_glob = stats_glob_.as<double>();
   stats_fused_ = false;
-  if (comm_ && comm_->nranks > 1 && peer_ready_) {
+  if (allow_fused && comm_ && comm_->nranks > 1 && peer_ready_) {
     // a peer may still be inside a long evaluation kernel: allow about a minute of skew
     fill_peer_box(&ts.box, 120000000000ll);
     ts.seq = ++stats_seq_;
@@ -785,6 +790,7 @@ Engine::heuristic_classify_stage(double epsrel, double last_estimate, double ite
   tracker_.reset(epsrel, 0.0);
   for (int k = 0; k < 3; ++k)
     tracker_.store(last_estimate);
+  PGN_TRY(agree_mem_capacity());
   HeuristicOutcome hs;
   PGN_TRY(heuristic_classify(n_, 0.0, iter_errorest, iter_finished_errorest, total_finished_errorest, &hs, true));
   std::memset(out, 0, sizeof *out);
@@ -962,6 +968,193 @@ Engine::split()
   cur_ = nxt;
   n_ = 2 * m;
   filtered_pending_ = false;
+  return PGN_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// stage API on caller-owned device arrays (reference layouts: bounds [ndim][n], flags as doubles)
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void
+k_fill_f64(double* x, size_t n, double v)
+{
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    x[i] = v;
+}
+// Region_characteristics::active_regions is an array of doubles in the reference (0. / 1.)
+__global__ void
+k_flags_from_f64(const double* __restrict__ f, uint8_t* __restrict__ out, size_t n)
+{
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[i] = f[i] != 0.0 ? 1 : 0;
+}
+}  // namespace
+
+int
+Engine::dev_uniform_split(int parts, double* d_left, double* d_length, size_t n)
+{
+  if (parts < 1 || (!d_left || !d_length))
+    return PGN_ERR_INVALID;
+  PGN_CUDA(cudaSetDevice(device_));
+  double total = 1.0;
+  for (int d = 0; d < ndim_; ++d)
+    total *= parts;
+  if (static_cast<double>(n) != total)
+    return PGN_ERR_INVALID;
+  ++launches_, k_uniform_split<<<blocks_for(n, 512), 512, 0, stream_>>>(d_left, d_length, n, parts, ndim_,
+                                                                         1. / static_cast<double>(parts));
+  PGN_CUDA(cudaGetLastError());
+  PGN_CUDA(cudaStreamSynchronize(stream_));
+  return PGN_OK;
+}
+
+int
+Engine::dev_evaluate(pgn_eval_fn fn, void* user, const double* d_left, const double* d_length, size_t n,
+                     double* d_est, double* d_err, int32_t* d_axis, double* d_active_f64, double* sum_est,
+                     double* sum_err)
+{
+  if (!fn || ((!d_left || !d_length || !d_est || !d_err || !d_axis) && n > 0))
+    return PGN_ERR_INVALID;
+  PGN_CUDA(cudaSetDevice(device_));
+  PGN_TRY(ensure_iteration_buffers(n));
+  if (n > 0) {
+    PGN_TRY(launch_evaluate_on(fn, user, d_left, d_length, n, d_est, d_err, d_axis));
+    // apply_cubature_integration_rules resets every flag to active (PaganiUtils.cuh:310-311)
+    if (d_active_f64)
+      ++launches_, k_fill_f64<<<blocks_for(n, 256), 256, 0, stream_>>>(d_active_f64, n, 1.0);
+    // the two sums it returns (:336-341): one pass of the classify kernel without refinement
+    TileScratch ts = make_scratch(false);
+    ++launches_, k_classify<false><<<super_tiles_for(tiles_for(n)), kBlock, 0, stream_>>>(
+      d_est, d_err, nullptr, nullptr, active_.as<uint8_t>(), n, 0.0, 0, static_cast<unsigned int>(tiles_for(n)), ts);
+    PGN_CUDA(cudaGetLastError());
+    PGN_CUDA(cudaMemcpyAsync(host_local_, stats_dev_.ptr, sizeof(double) * kStatsLen, cudaMemcpyDeviceToHost,
+                             stream_));
+  }
+  PGN_CUDA(cudaStreamSynchronize(stream_));
+  if (sum_est)
+    *sum_est = n > 0 ? host_local_[kSumEst] : 0.0;
+  if (sum_err)
+    *sum_err = n > 0 ? host_local_[kSumErr] : 0.0;
+  return PGN_OK;
+}
+
+// Sub_regions_filter::get_num_active_regions (Sub_region_filter.cuh:61-82); leaves the tile prefix for dev_filter
+int
+Engine::dev_count_active(const double* d_active_f64, size_t n, size_t* count)
+{
+  if (!count || (!d_active_f64 && n > 0))
+    return PGN_ERR_INVALID;
+  PGN_CUDA(cudaSetDevice(device_));
+  *count = 0;
+  if (n == 0)
+    return PGN_OK;
+  PGN_TRY(ensure_iteration_buffers(n));
+  ++launches_, k_flags_from_f64<<<blocks_for(n, 256), 256, 0, stream_>>>(d_active_f64, active_.as<uint8_t>(), n);
+  TileScratch ts = make_scratch(false);
+  // the flag array doubles as the (unused) value arrays of the counting kernel
+  ++launches_, k_recount<<<tiles_for(n), kBlock, 0, stream_>>>(d_active_f64, d_active_f64, active_.as<uint8_t>(), n,
+                                                                ts);
+  PGN_CUDA(cudaGetLastError());
+  PGN_CUDA(cudaMemcpyAsync(host_local_, stats_dev_.ptr, sizeof(double) * kStatsLen, cudaMemcpyDeviceToHost,
+                           stream_));
+  PGN_CUDA(cudaStreamSynchronize(stream_));
+  *count = static_cast<size_t>(host_local_[kNumActive]);
+  return PGN_OK;
+}
+
+// Sub_regions_filter::filter (Sub_region_filter.cuh:85-139) into caller-allocated arrays of m survivors
+int
+Engine::dev_filter(const double* d_left, const double* d_length, const double* d_est, const double* d_err,
+                   const int32_t* d_axis, const double* d_active_f64, size_t n, size_t m, double* out_left,
+                   double* out_length, double* out_est, double* out_err, int32_t* out_axis)
+{
+  if (n == 0 || m == 0)
+    return PGN_OK;
+  if (!d_left || !d_length || !d_est || !d_err || !d_axis || !d_active_f64 || !out_left || !out_length ||
+      !out_est || !out_err || !out_axis)
+    return PGN_ERR_INVALID;
+  size_t counted = 0;
+  PGN_TRY(dev_count_active(d_active_f64, n, &counted));
+  if (counted != m) {
+    set_last_error("dev_filter: the output arrays are sized for a different number of survivors");
+    return PGN_ERR_INVALID;
+  }
+  CompactArgs A;
+  A.left = d_left;
+  A.length = d_length;
+  A.est = d_est;
+  A.err = d_err;
+  A.axis = d_axis;
+  A.active = active_.as<uint8_t>();
+  A.tile_offset = tile_offset_.as<uint64_t>();
+  A.n = n;
+  A.m = m;
+  A.out_left = out_left;
+  A.out_length = out_length;
+  A.parent_est = out_est;
+  A.parent_err = out_err;
+  A.out_axis = out_axis;
+  A.ndim = ndim_;
+  ++launches_, k_compact<false><<<tiles_for(n), kBlock, 0, stream_>>>(A);
+  PGN_CUDA(cudaGetLastError());
+  PGN_CUDA(cudaStreamSynchronize(stream_));
+  return PGN_OK;
+}
+
+// Sub_region_splitter::split (Sub_region_splitter.cuh:55-87): m parents -> 2m children at j and m + j
+int
+Engine::dev_split(const double* d_left, const double* d_length, const int32_t* d_axis, size_t m, double* out_left,
+                  double* out_length)
+{
+  if (m == 0)
+    return PGN_OK;
+  if (!d_left || !d_length || !d_axis || !out_left || !out_length)
+    return PGN_ERR_INVALID;
+  PGN_CUDA(cudaSetDevice(device_));
+  ++launches_, k_split<<<blocks_for(m, kBlock), kBlock, 0, stream_>>>(d_left, d_length, d_axis, m, ndim_, out_left,
+                                                                       out_length);
+  PGN_CUDA(cudaGetLastError());
+  PGN_CUDA(cudaStreamSynchronize(stream_));
+  return PGN_OK;
+}
+
+int
+Engine::regions_import_device(const double* d_left, const double* d_length, size_t n)
+{
+  if ((!d_left || !d_length) && n > 0)
+    return PGN_ERR_INVALID;
+  PGN_CUDA(cudaSetDevice(device_));
+  PGN_TRY(left_[cur_].reserve(sizeof(double) * std::max<size_t>(n, 1) * ndim_));
+  PGN_TRY(length_[cur_].reserve(sizeof(double) * std::max<size_t>(n, 1) * ndim_));
+  if (n > 0) {
+    PGN_CUDA(cudaMemcpyAsync(left_[cur_].ptr, d_left, sizeof(double) * n * ndim_, cudaMemcpyDeviceToDevice, stream_));
+    PGN_CUDA(cudaMemcpyAsync(length_[cur_].ptr, d_length, sizeof(double) * n * ndim_, cudaMemcpyDeviceToDevice,
+                             stream_));
+    PGN_CUDA(cudaStreamSynchronize(stream_));
+  }
+  n_ = n;
+  parents_n_ = 0;
+  evaluated_ = classified_ = filtered_pending_ = false;
+  return PGN_OK;
+}
+
+int
+Engine::regions_export_device(double* d_left, double* d_length, size_t cap, size_t* n)
+{
+  if (n)
+    *n = n_;
+  if (cap < n_)
+    return d_left || d_length ? PGN_ERR_INVALID : PGN_OK;
+  PGN_CUDA(cudaSetDevice(device_));
+  if (n_ > 0 && d_left)
+    PGN_CUDA(cudaMemcpyAsync(d_left, left_[cur_].ptr, sizeof(double) * n_ * ndim_, cudaMemcpyDeviceToDevice, stream_));
+  if (n_ > 0 && d_length)
+    PGN_CUDA(cudaMemcpyAsync(d_length, length_[cur_].ptr, sizeof(double) * n_ * ndim_, cudaMemcpyDeviceToDevice,
+                             stream_));
+  PGN_CUDA(cudaStreamSynchronize(stream_));
   return PGN_OK;
 }
 
@@ -1171,9 +1364,30 @@ Engine::mem_capacity_bytes() const
     size_t held = 0;
     for (const DeviceBuf* b : mine)
       held += b->bytes;
-    return frac * static_cast<double>(f + held) * (comm_ ? comm_->nranks : 1);
+    return frac * static_cast<double>(f + held);
   }
   return 16e9;  // heuristic_classifier.cuh:89-94
+}
+
+// The capacity every rank bases its heuristic decisions on.  PGN_MEM_PARITY: the reference's constant.
+// PGN_MEM_NATIVE: ranks x the SMALLEST per-rank figure, agreed once per call through a MIN all-reduce -- ranks that
+// derived `criteria` / `must_terminate` from their own free memory could disagree on entering the (collective)
+// heuristic path and dead-lock in it.
+int
+Engine::agree_mem_capacity()
+{
+  double mine = mem_capacity_bytes();
+  const int w = comm_ ? comm_->nranks : 1;
+  if (opts_.mem_mode == PGN_MEM_NATIVE && w > 1) {
+    double neg = -mine;
+    PGN_CUDA(cudaMemcpyAsync(stats_glob_.ptr, &neg, sizeof neg, cudaMemcpyHostToDevice, stream_));
+    PGN_TRY(comm_->allreduce(stats_glob_.as<double>(), 1, kOpMax, stream_));
+    PGN_CUDA(cudaMemcpyAsync(&neg, stats_glob_.ptr, sizeof neg, cudaMemcpyDeviceToHost, stream_));
+    PGN_CUDA(cudaStreamSynchronize(stream_));
+    mine = -neg * w;
+  }
+  mem_capacity_ = mine;
+  return PGN_OK;
 }
 
 int
@@ -1186,7 +1400,7 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
   const size_t doubles = n_global * (10 * nd + 8);
   const size_t ints = 4 * n_global;
   const size_t required = 8 * doubles + 4 * ints;
-  const size_t total = static_cast<size_t>(mem_capacity_bytes());
+  const size_t total = static_cast<size_t>(mem_capacity_);
   const size_t free_mem = total > required ? total - required : 1;
   const double ratio = static_cast<double>(required) / static_cast<double>(free_mem);
   const bool necessary = ratio > 1.;
@@ -1421,6 +1635,7 @@ Engine::integrate(pgn_eval_fn fn, void* user, const pgn_integrate_args& args, pg
     return PGN_ERR_STATE;
   }
   parents_n_ = 0;  // the reference starts every call without parent estimates (:165, :375)
+  PGN_TRY(agree_mem_capacity());
 
   size_t n_global = n_;
   if (multi) {
@@ -1436,6 +1651,25 @@ Engine::integrate(pgn_eval_fn fn, void* user, const pgn_integrate_args& args, pg
   uint64_t nregions = 0, iters = 0, neval = 0;
   int status = 1;
   bool done = false;
+  // Stage timing: six events per iteration from a grow-only pool, resolved once after the loop (an event
+  // synchronisation per iteration would add a host round trip to every iteration of a traced run).
+  enum { kEvStart = 0, kEvEvaluated, kEvClassified, kEvHeuristicBegin, kEvHeuristicEnd, kEvSplit, kEvPerIter };
+  std::vector<unsigned char> ev_recorded;
+  auto mark = [&](int it, int k) {
+    if (!tracing)
+      return;
+    const size_t idx = static_cast<size_t>(it) * kEvPerIter + k;
+    while (ev_pool_.size() <= idx) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreate(&e) != cudaSuccess)
+        return;
+      ev_pool_.push_back(e);
+    }
+    if (ev_recorded.size() <= idx)
+      ev_recorded.resize(idx + 1, 0);
+    if (cudaEventRecord(ev_pool_[idx], stream_) == cudaSuccess)
+      ev_recorded[idx] = 1;
+  };
 
   for (int it = 0; it < max_iters && n_global > 0 && !done; ++it) {
     pgn_iter_stats st;
@@ -1444,15 +1678,12 @@ Engine::integrate(pgn_eval_fn fn, void* user, const pgn_integrate_args& args, pg
     st.nregions = n_;
     st.nregions_global = n_global;
 
-    if (tracing)
-      cudaEventRecord(ev_[0], stream_);
+    mark(it, kEvStart);
     PGN_TRY(launch_evaluate(fn, user));
     evaluated_ = true;
-    if (tracing)
-      cudaEventRecord(ev_[1], stream_);
+    mark(it, kEvEvaluated);
     PGN_TRY(run_classify(epsrel, relerr));
-    if (tracing)
-      cudaEventRecord(ev_[2], stream_);
+    mark(it, kEvClassified);
     PGN_TRY(sync_stats(false));
     neval += static_cast<uint64_t>(n_global) * rule_.feval;
 
@@ -1461,13 +1692,6 @@ Engine::integrate(pgn_eval_fn fn, void* user, const pgn_integrate_args& args, pg
     if (opts_.trace_arrays) {
       digest_arrays(&st, false);
       digest_arrays(&st, true);
-    }
-    if (tracing) {
-      float ms = 0;
-      cudaEventElapsedTime(&ms, ev_[0], ev_[1]);
-      st.eval_ms = ms;
-      cudaEventElapsedTime(&ms, ev_[1], ev_[2]);
-      st.classify_ms = ms;
     }
     st.iter_estimate = iter_est;
     st.iter_errorest = iter_err;
@@ -1515,11 +1739,9 @@ Engine::integrate(pgn_eval_fn fn, void* user, const pgn_integrate_args& args, pg
     }
 
     HeuristicOutcome hs;
-    if (tracing)
-      cudaEventRecord(ev_[2], stream_);
+    mark(it, kEvHeuristicBegin);
     PGN_TRY(heuristic_classify(n_global, iter_est, iter_err, fin_err, cum_err, &hs));
-    if (tracing)
-      cudaEventRecord(ev_[3], stream_);
+    mark(it, kEvHeuristicEnd);
     st.heuristic_ran = hs.ran;
     st.heuristic_probes = hs.probes;
     st.threshold = hs.threshold;
@@ -1539,13 +1761,8 @@ Engine::integrate(pgn_eval_fn fn, void* user, const pgn_integrate_args& args, pg
       st.cum_estimate = cum_est;
       st.cum_errorest = cum_err;
       st.nactive = m_global;
-      if (tracing) {
-        cudaEventSynchronize(ev_[3]);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ev_[2], ev_[3]);
-        st.heuristic_ms = ms;
+      if (tracing)
         trace_.push_back(st);
-      }
       done = true;
       break;
     }
@@ -1570,16 +1787,9 @@ Engine::integrate(pgn_eval_fn fn, void* user, const pgn_integrate_args& args, pg
       st.rebalanced = rebalanced;
       n_global = 2 * m_global;
     }
-    if (tracing) {
-      cudaEventRecord(ev_[4], stream_);
-      cudaEventSynchronize(ev_[4]);
-      float ms = 0;
-      cudaEventElapsedTime(&ms, ev_[2], ev_[3]);
-      st.heuristic_ms = ms;
-      cudaEventElapsedTime(&ms, ev_[3], ev_[4]);
-      st.split_ms = ms;
+    mark(it, kEvSplit);
+    if (tracing)
       trace_.push_back(st);
-    }
     evaluated_ = classified_ = false;
     if (args.iters_mode == PGN_ITERS_AFTER_SPLIT)
       iters++;
@@ -1587,6 +1797,22 @@ Engine::integrate(pgn_eval_fn fn, void* user, const pgn_integrate_args& args, pg
   if (!done)
     nregions += n_global;
   PGN_CUDA(cudaStreamSynchronize(stream_));
+  if (tracing) {
+    auto elapsed = [&](int it, int a, int b) -> double {
+      const size_t ia = static_cast<size_t>(it) * kEvPerIter + a, ib = static_cast<size_t>(it) * kEvPerIter + b;
+      if (ib >= ev_recorded.size() || !ev_recorded[ia] || !ev_recorded[ib])
+        return 0.0;
+      float ms = 0;
+      return cudaEventElapsedTime(&ms, ev_pool_[ia], ev_pool_[ib]) == cudaSuccess ? ms : 0.0;
+    };
+    for (pgn_iter_stats& t : trace_) {
+      const int it = static_cast<int>(t.iteration);
+      t.eval_ms = elapsed(it, kEvStart, kEvEvaluated);
+      t.classify_ms = elapsed(it, kEvEvaluated, kEvClassified);
+      t.heuristic_ms = elapsed(it, kEvHeuristicBegin, kEvHeuristicEnd);
+      t.split_ms = elapsed(it, kEvHeuristicEnd, kEvSplit);
+    }
+  }
 
   out->estimate = cum_est;
   out->errorest = cum_err;

@@ -78,6 +78,21 @@ public:
 
   int integrate(pgn_eval_fn fn, void* user, const pgn_integrate_args& args, pgn_result_t* out);
 
+  // ---- the same stages on CALLER-OWNED device arrays in the reference's layouts (what its stage objects
+  // Cubature_rules / Sub_regions_filter / Sub_region_splitter bind to; include/pagani_b200/compat)
+  int dev_uniform_split(int parts, double* d_left, double* d_length, size_t n);
+  int dev_evaluate(pgn_eval_fn fn, void* user, const double* d_left, const double* d_length, size_t n,
+                   double* d_est, double* d_err, int32_t* d_axis, double* d_active_f64, double* sum_est,
+                   double* sum_err);
+  int dev_count_active(const double* d_active_f64, size_t n, size_t* count);
+  int dev_filter(const double* d_left, const double* d_length, const double* d_est, const double* d_err,
+                 const int32_t* d_axis, const double* d_active_f64, size_t n, size_t m, double* out_left,
+                 double* out_length, double* out_est, double* out_err, int32_t* out_axis);
+  int dev_split(const double* d_left, const double* d_length, const int32_t* d_axis, size_t m, double* out_left,
+                double* out_length);
+  int regions_import_device(const double* d_left, const double* d_length, size_t n);
+  int regions_export_device(double* d_left, double* d_length, size_t cap, size_t* n);
+
   int comm_init_nccl(const uint8_t* id, int nranks, int rank);
   int comm_init_host(int nranks, int rank, pgn_allreduce_fn ar, pgn_alltoallv_fn a2a, void* user);
   int comm_size(int* nranks, int* rank) const;
@@ -95,6 +110,8 @@ public:
 private:
   // ---- stage helpers (all enqueue on stream_)
   int launch_evaluate(pgn_eval_fn fn, void* user);
+  int launch_evaluate_on(pgn_eval_fn fn, void* user, const double* left, const double* length, size_t n,
+                         double* est, double* err, int32_t* axis);
   // reduce + (all-reduce) + read back; fills host_local_/host_global_
   int run_classify(double epsrel, int relerr);
   int run_threshold(int mode, double threshold);
@@ -122,7 +139,9 @@ private:
                          double cum_err, HeuristicOutcome* out, bool force = false);
   // bucket partition of the current errors for the device-side threshold search
   int prepare_search(const struct BucketPlan& plan, struct BucketTables* tables);
-  double mem_capacity_bytes() const;
+  double mem_capacity_bytes() const;  // this rank's figure
+  int agree_mem_capacity();            // -> mem_capacity_, identical on every rank
+  double mem_capacity_ = 16e9;
 
   int ndim_;
   pgn_opts opts_;
@@ -172,7 +191,7 @@ private:
   unsigned long long peer_seq_ = 0;      // probes exchanged so far (identical on every rank)
   unsigned long long stats_seq_ = 0;     // fused statistics all-reduces so far
   bool stats_fused_ = false;             // the last statistics kernel already produced the global vector
-  struct TileScratch make_scratch();
+  struct TileScratch make_scratch(bool allow_fused = true);  // false: rank-local statistics (stage API)
   void fill_peer_box(struct PeerBox* box, long long spin_limit) const;
 
   ConvergenceTracker tracker_;
@@ -185,7 +204,7 @@ private:
 
   uint64_t launches_ = 0;  // kernels of this library enqueued so far (bench.py's gpu_launches)
   std::vector<pgn_iter_stats> trace_;
-  cudaEvent_t ev_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> ev_pool_;  // stage-timing events of a traced integrate(): six per iteration
 };
 
 }  // namespace pgn

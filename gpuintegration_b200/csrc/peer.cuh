@@ -1,17 +1,22 @@
 // In-kernel all-reduce over NVLink peer memory (several ranks, one process per GPU).
 //
 // Every rank owns a small mailbox in its HBM that all peers can write (mapped with cudaIpc over
-// NVLink 5 / NVSwitch).  For exchange number s a rank stores its contribution into slot
-// [s & 1][own rank] of EVERY peer's mailbox, fences, then raises that slot's flag to s; it then waits
-// until all slots of its own mailbox carry flag s and combines the contributions in rank order, so
-// every rank obtains bit-identical totals without the host and without a separate collective launch.
-// Two slots per peer are enough: a rank can only start exchange s + 1 after it has read every
-// contribution of exchange s, and a peer needs that rank's s + 1 before it can move on to s + 2.
+// NVLink 5 / NVSwitch).  A contribution travels as self-validating 8-byte PACKETS: the low word is
+// 32 bits of payload, the high word the number of the exchange.  An aligned 8-byte store is
+// single-copy atomic, so a receiver that sees the expected exchange number in a packet also sees
+// its payload: no fence, no separate flag, no second round trip -- an exchange costs one NVLink
+// one-way latency instead of a system-scope fence (which waits for the write acknowledgements)
+// plus a flag store.  For exchange number s a rank stores its packets into slot [s & 1][own rank]
+// of EVERY peer's mailbox, then polls the slots [s & 1][q] of its own mailbox and combines the
+// contributions in rank order, so every rank obtains bit-identical totals without the host and
+// without a separate collective launch.  Two slots per peer are enough: a rank can only start
+// exchange s + 1 after it has read every contribution of exchange s, and a peer needs that rank's
+// s + 1 before it can move on to s + 2.
 //
 // Two independent channels share one mailbox allocation:
-//   search channel  (3 doubles)  per probe of the heuristic threshold search (threshold_search.cuh)
-//   stats channel   (32 doubles) the iteration statistics, fused into the last block of the
-//                                classify / threshold kernels (stages.cuh, dev::finalize)
+//   search channel  (kBoxDoubles)    probes of the heuristic threshold search (threshold_search.cuh)
+//   stats channel   (kStatsDoubles)  the iteration statistics, fused into the last block of the
+//                                    classify / threshold kernels (stages.cuh, dev::finalize)
 // The reference has no multi-GPU path; NCCL remains the transport for bulk region rebalancing.
 #ifndef PGN_PEER_CUH
 #define PGN_PEER_CUH
@@ -19,19 +24,18 @@
 #include <cuda_runtime.h>
 
 #include <cstddef>
+#include <cstdint>
 
 namespace pgn {
 
 constexpr int kMaxPeers = 16;
-constexpr int kBoxDoubles = 4;     // search channel, per slot
+constexpr int kBoxDoubles = 8;     // search channel, per slot
 constexpr int kStatsDoubles = 32;  // stats channel, per slot (= kStatsLen of stages.cuh)
 
-// byte offsets inside a mailbox
-constexpr size_t kBoxDataOff = 0;
-constexpr size_t kBoxFlagOff = kBoxDataOff + sizeof(double) * 2 * kMaxPeers * kBoxDoubles;
-constexpr size_t kStatsDataOff = kBoxFlagOff + sizeof(unsigned long long) * 2 * kMaxPeers;
-constexpr size_t kStatsFlagOff = kStatsDataOff + sizeof(double) * 2 * kMaxPeers * kStatsDoubles;
-constexpr size_t kMailboxBytes = kStatsFlagOff + sizeof(unsigned long long) * 2 * kMaxPeers;
+// byte offsets inside a mailbox: [2 parities][kMaxPeers senders][2 packets per double]
+constexpr size_t kBoxOff = 0;
+constexpr size_t kStatsOff = kBoxOff + sizeof(unsigned long long) * 2 * kMaxPeers * 2 * kBoxDoubles;
+constexpr size_t kMailboxBytes = kStatsOff + sizeof(unsigned long long) * 2 * kMaxPeers * 2 * kStatsDoubles;
 
 struct PeerBox {
   char* base[kMaxPeers];  // base[q]: peer q's mailbox (own rank: the local allocation)
@@ -39,119 +43,110 @@ struct PeerBox {
   long long spin_limit;   // clock64() ticks before giving up (a lost peer must not hang the GPU for ever)
 };
 
-__device__ __forceinline__ double*
-box_data(const PeerBox& b, int q)
+// exchange number -> packet tag (never 0: a zeroed mailbox matches no exchange)
+__device__ __forceinline__ uint32_t
+packet_tag(unsigned long long seq)
 {
-  return reinterpret_cast<double*>(b.base[q] + kBoxDataOff);
-}
-__device__ __forceinline__ unsigned long long*
-box_flag(const PeerBox& b, int q)
-{
-  return reinterpret_cast<unsigned long long*>(b.base[q] + kBoxFlagOff);
-}
-__device__ __forceinline__ double*
-stats_data(const PeerBox& b, int q)
-{
-  return reinterpret_cast<double*>(b.base[q] + kStatsDataOff);
-}
-__device__ __forceinline__ unsigned long long*
-stats_flag(const PeerBox& b, int q)
-{
-  return reinterpret_cast<unsigned long long*>(b.base[q] + kStatsFlagOff);
+  return static_cast<uint32_t>(seq % 0xffffffffull) + 1u;
 }
 
-// Sum of three doubles over the ranks.  Block-collective (any block size >= nranks); returns false
-// (in every thread) when a peer did not answer in time.
+// All-reduce of W doubles over the ranks through the channel at byte offset `off` (kBoxOff / kStatsOff, whose
+// slots hold `slot_doubles` doubles).  `mine`: this rank's contribution (shared or global memory, read by all
+// threads); `s_recv`: shared scratch of kMaxPeers * 2 * W words.  Block-collective; afterwards
+// s_recv[(q * W + j) * 2 + {0,1}] holds the two halves of rank q's j-th value.  Returns false (in every thread)
+// when a peer did not answer in time.
+template <int W>
 __device__ __forceinline__ bool
-peer_allreduce3(const PeerBox& box, unsigned long long seq, double& a, double& b, double& c, int* s_ok)
+peer_exchange(const PeerBox& box, size_t off, int slot_doubles, unsigned long long seq, const double* mine,
+              uint32_t* s_recv, int* s_ok)
 {
   const int par = static_cast<int>(seq & 1ull);
+  const uint32_t tag = packet_tag(seq);
   if (threadIdx.x == 0)
     *s_ok = 1;
   __syncthreads();
-  if (static_cast<int>(threadIdx.x) < box.nranks) {
-    const int q = threadIdx.x;
-    volatile double* slot = box_data(box, q) + (par * kMaxPeers + box.rank) * kBoxDoubles;
-    slot[0] = a;
-    slot[1] = b;
-    slot[2] = c;
-    __threadfence_system();
-    *reinterpret_cast<volatile unsigned long long*>(box_flag(box, q) + par * kMaxPeers + box.rank) = seq;
-    // wait for peer q's contribution to arrive in OUR mailbox
-    volatile unsigned long long* mine = box_flag(box, box.rank) + par * kMaxPeers + q;
+  const int total = box.nranks * 2 * W;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int q = idx / (2 * W), k = idx - q * (2 * W);
+    const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(mine[k >> 1]));
+    const uint32_t half = (k & 1) ? static_cast<uint32_t>(bits >> 32) : static_cast<uint32_t>(bits);
+    volatile unsigned long long* dst = reinterpret_cast<volatile unsigned long long*>(box.base[q] + off) +
+                                       (static_cast<size_t>(par) * kMaxPeers + box.rank) * 2 * slot_doubles + k;
+    *dst = (static_cast<unsigned long long>(tag) << 32) | half;
+  }
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int q = idx / (2 * W), k = idx - q * (2 * W);
+    const volatile unsigned long long* src =
+      reinterpret_cast<const volatile unsigned long long*>(box.base[box.rank] + off) +
+      (static_cast<size_t>(par) * kMaxPeers + q) * 2 * slot_doubles + k;
     const long long t0 = clock64();
-    while (*mine < seq) {
+    unsigned long long pkt = *src;
+    while (static_cast<uint32_t>(pkt >> 32) != tag) {
       if (clock64() - t0 > box.spin_limit) {
         *s_ok = 0;
         break;
       }
+      pkt = *src;
     }
-    __threadfence_system();
+    s_recv[idx] = static_cast<uint32_t>(pkt);
   }
   __syncthreads();
-  const bool ok = *s_ok != 0;
-  double ta = 0.0, tb = 0.0, tc = 0.0;
-  if (ok) {
-    const volatile double* base = box_data(box, box.rank) + par * kMaxPeers * kBoxDoubles;
-    for (int q = 0; q < box.nranks; ++q) {
-      ta += base[q * kBoxDoubles + 0];
-      tb += base[q * kBoxDoubles + 1];
-      tc += base[q * kBoxDoubles + 2];
-    }
-  }
+  return *s_ok != 0;
+}
+
+__device__ __forceinline__ double
+peer_value(const uint32_t* s_recv, int W, int q, int j)
+{
+  const uint32_t lo = s_recv[(q * W + j) * 2], hi = s_recv[(q * W + j) * 2 + 1];
+  return __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(hi) << 32) | lo));
+}
+
+// Sum of W <= kBoxDoubles doubles over the ranks (rank order: identical totals everywhere).  Block-collective
+// (any block size); `s_mine` [W] and `s_recv` [kMaxPeers * 2 * W] are shared scratch.  Returns false (in every
+// thread) when a peer did not answer in time.
+template <int W>
+__device__ __forceinline__ bool
+peer_allreduce_sum(const PeerBox& box, unsigned long long seq, double (&v)[W], double* s_mine, uint32_t* s_recv,
+                   int* s_ok)
+{
+  static_assert(W <= kBoxDoubles, "search channel slot too small");
+  __syncthreads();  // s_mine / s_recv of the previous exchange have been consumed
+  if (threadIdx.x < W)
+    s_mine[threadIdx.x] = v[threadIdx.x];
   __syncthreads();
-  a = ta;
-  b = tb;
-  c = tc;
+  const bool ok = peer_exchange<W>(box, kBoxOff, kBoxDoubles, seq, s_mine, s_recv, s_ok);
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    double t = 0.0;
+    if (ok)
+      for (int q = 0; q < box.nranks; ++q)
+        t += peer_value(s_recv, W, q, j);
+    v[j] = t;
+  }
   return ok;
 }
 
 // All-reduce of the kStatsDoubles-vector `local` into `global` (both in this rank's memory): SUM in
 // rank order for every slot except [max_lo, max_hi), which take the maximum.  Block-collective, the
-// block must have at least 32 threads.  On a time-out the vector is filled with NaN (the host driver
-// notices) and false is returned.
+// block must have at least kStatsDoubles threads.  On a time-out the vector is filled with NaN (the
+// host driver notices) and false is returned.
 __device__ __forceinline__ bool
 peer_allreduce_stats(const PeerBox& box, unsigned long long seq, const double* local, double* global,
                      int max_lo, int max_hi, int* s_ok)
 {
-  const int par = static_cast<int>(seq & 1ull);
-  if (threadIdx.x == 0)
-    *s_ok = 1;
-  __syncthreads();
-  // thread t writes element t % 32 to peers t / 32, t / 32 + blockDim / 32, ...
-  const int elem = threadIdx.x & 31;
-  const double mine_v = local[elem];
-  for (int q = threadIdx.x >> 5; q < box.nranks; q += blockDim.x >> 5) {
-    volatile double* slot = stats_data(box, q) + (par * kMaxPeers + box.rank) * kStatsDoubles;
-    slot[elem] = mine_v;
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (static_cast<int>(threadIdx.x) < box.nranks) {
-    const int q = threadIdx.x;
-    *reinterpret_cast<volatile unsigned long long*>(stats_flag(box, q) + par * kMaxPeers + box.rank) = seq;
-    volatile unsigned long long* arrived = stats_flag(box, box.rank) + par * kMaxPeers + q;
-    const long long t0 = clock64();
-    while (*arrived < seq) {
-      if (clock64() - t0 > box.spin_limit) {
-        *s_ok = 0;
-        break;
-      }
-    }
-    __threadfence_system();
-  }
-  __syncthreads();
-  const bool ok = *s_ok != 0;
+  __shared__ uint32_t s_stats_recv[kMaxPeers * 2 * kStatsDoubles];
+  __syncthreads();  // `local` was written by this block
+  const bool ok = peer_exchange<kStatsDoubles>(box, kStatsOff, kStatsDoubles, seq, local, s_stats_recv, s_ok);
   if (threadIdx.x < kStatsDoubles) {
     double acc;
     if (!ok) {
       acc = __longlong_as_double(0x7ff8000000000000LL);
     } else {
-      const volatile double* base = stats_data(box, box.rank) + par * kMaxPeers * kStatsDoubles;
-      const bool is_max = static_cast<int>(threadIdx.x) >= max_lo && static_cast<int>(threadIdx.x) < max_hi;
-      acc = base[threadIdx.x];
+      const int j = threadIdx.x;
+      const bool is_max = j >= max_lo && j < max_hi;
+      acc = peer_value(s_stats_recv, kStatsDoubles, 0, j);
       for (int q = 1; q < box.nranks; ++q) {
-        const double v = base[q * kStatsDoubles + threadIdx.x];
+        const double v = peer_value(s_stats_recv, kStatsDoubles, q, j);
         acc = is_max ? fmax(acc, v) : acc + v;
       }
     }

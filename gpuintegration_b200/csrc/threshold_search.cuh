@@ -453,6 +453,8 @@ k_search(BucketPlan plan, BucketTables T, SearchIO* io, PeerBox box)
 {
   __shared__ unsigned long long s_red[32][3];
   __shared__ int s_ok;
+  __shared__ double s_mine[3];
+  __shared__ uint32_t s_recv[kMaxPeers * 2 * 3];
   __shared__ unsigned long long c_key[kProbeCache];
   __shared__ unsigned long long c_cnt[kProbeCache];
   __shared__ double c_sum[kProbeCache];
@@ -498,8 +500,9 @@ k_search(BucketPlan plan, BucketTables T, SearchIO* io, PeerBox box)
         } else {
           probe_above(threshold, plan, T, s_red, &num_active, &active_err_sum);
           if (MULTI) {
-            double cnt = static_cast<double>(num_active), sum = active_err_sum, outside = outside_local;
-            const bool ok = peer_allreduce3(box, ++seq, cnt, sum, outside, &s_ok);
+            double v[3] = {static_cast<double>(num_active), active_err_sum, outside_local};
+            const bool ok = peer_allreduce_sum<3>(box, ++seq, v, s_mine, s_recv, &s_ok);
+            const double cnt = v[0], sum = v[1], outside = v[2];
             if (!ok || outside != 0.0) {
               if (threadIdx.x == 0) {
                 io->probes = ok ? -2 : -1;

@@ -193,6 +193,29 @@ int pgn_heuristic_classify(pgn_ctx* ctx, double epsrel, double last_estimate, do
 int pgn_fetch_estimates(pgn_ctx* ctx, double* estimate, double* errorest, int32_t* axis, uint8_t* active, size_t cap);
 int pgn_fetch_parents(pgn_ctx* ctx, double* estimate, double* errorest, int32_t* axis, size_t cap, size_t* n);
 
+/* ---- the same stages on CALLER-OWNED device arrays ----------------------------------------------
+ * What the reference's stage objects own and hand to each other: bounds as [ndim][n] doubles
+ * (Sub_regions::dLeftCoord / dLength, Sub_regions.cuh:38-258), estimates (Region_estimates.cuh:8-38), split axes as
+ * int and active flags as DOUBLES 0./1. (Region_characteristics.cuh:7-27).  include/pagani_b200/compat/ builds the
+ * reference's classes (Cubature_rules, Sub_regions_filter, Sub_region_splitter ...) on these, so that code written
+ * against the reference's stage interface -- its own unit tests -- compiles with only the include path changed.
+ * Every call is synchronous (the reference's stages end in cudaDeviceSynchronize). */
+int pgn_dev_uniform_split(pgn_ctx* ctx, int parts_per_axis, double* d_left, double* d_length,
+                          size_t n /* = parts^ndim */); /* create_uniform_split, Sub_regions.cuh:11-36 */
+int pgn_dev_evaluate(pgn_ctx* ctx, pgn_eval_fn fn, void* user, const double* d_left, const double* d_length, size_t n,
+                     double* d_estimate, double* d_errorest, int32_t* d_axis, double* d_active /* set to 1., may be NULL */,
+                     double* sum_estimate, double* sum_errorest); /* apply_cubature_integration_rules, PaganiUtils.cuh:291-343 */
+int pgn_dev_count_active(pgn_ctx* ctx, const double* d_active, size_t n,
+                         size_t* count); /* Sub_regions_filter::get_num_active_regions, Sub_region_filter.cuh:61-82 */
+int pgn_dev_filter(pgn_ctx* ctx, const double* d_left, const double* d_length, const double* d_estimate,
+                   const double* d_errorest, const int32_t* d_axis, const double* d_active, size_t n, size_t m /* survivors */,
+                   double* out_left, double* out_length, double* out_estimate, double* out_errorest,
+                   int32_t* out_axis); /* alignRegions, Sub_region_filter.cuh:8-47: stable compaction into [..][m] arrays */
+int pgn_dev_split(pgn_ctx* ctx, const double* d_left, const double* d_length, const int32_t* d_axis, size_t m,
+                  double* out_left, double* out_length); /* divideIntervalsGPU, Sub_region_splitter.cuh:8-46: [..][2m] */
+int pgn_regions_import_device(pgn_ctx* ctx, const double* d_left, const double* d_length, size_t n);
+int pgn_regions_export_device(pgn_ctx* ctx, double* d_left, double* d_length, size_t cap, size_t* n);
+
 /* ---- the whole loop (Workspace::integrate, Workspace.cuh:361-494 / :148-358) ------------------ */
 typedef struct pgn_integrate_args {
   double epsrel, epsabs;

@@ -57,6 +57,10 @@ constexpr int kWarpsPerBlock = PGN_EVAL_WARPS;
 #ifndef PGN_EVAL_QUAD
 #define PGN_EVAL_QUAD 0
 #endif
+// 1: double-buffer the coordinates of the point loop (loads of trip t+1 issued before the arithmetic of trip t)
+#ifndef PGN_EVAL_PIPELINE
+#define PGN_EVAL_PIPELINE 0
+#endif
 
 // Launch-bound tuning knob of the evaluation kernel: resident 128-thread blocks per SM the register
 // allocation must allow (4 -> up to 128 registers per thread, 7 -> 72, 8 -> 64).  Cheap integrands
@@ -121,6 +125,23 @@ struct BatchCall<F, N, M, true> {
     static_cast<const F*>(f)->template batch<M>(x, out);
   }
 };
+
+// Optional functor protocol, second form:
+//     template <int M> bool batch_fast(const double (&x)[M][N], double (&f)[M]) const
+// straight-line code with NO function call and no slow path: returns true when every f[m] equals
+// operator()(x[m]...) exactly, false when some argument needs the functor's slow path (f is then
+// meaningless).  The point loop calls it instead of batch/operator() and, in the rare case that a lane
+// reported false, re-evaluates the whole region afterwards with operator() (evaluate_region_exact, not
+// inlined).  Keeping the library's slow paths (calls into libdevice, their uniform-register clobbers and the
+// re-convergence points around them) out of the loop body lets the compiler keep every constant of the fast
+// path resident: for the oscillatory family that is 11 fewer instructions per trip.
+template <class F, int N, int M, class = void>
+struct has_batch_fast : std::false_type {};
+template <class F, int N, int M>
+struct has_batch_fast<F, N, M,
+                      std::void_t<decltype(std::declval<const F&>().template batch_fast<M>(
+                        std::declval<const double (&)[M][N]>(), std::declval<double (&)[M]>()))>>
+  : std::true_type {};
 
 struct EvalParams {
   const double* left;
@@ -278,8 +299,19 @@ region_epilogue(const EvalParams& P, size_t reg, int lane, const double* s_f, co
       const double f0 = s_f[0];
       const double fp = s_f[1 + 2 * lane], fm = s_f[2 + 2 * lane];
       const double gp = s_f[1 + 2 * lane + 2 * NDIM], gm = s_f[2 + 2 * lane + 2 * NDIM];
-      const double base = __dmul_rn(__dadd_rn(f0, f0), one_minus_ratio);
-      const double t = __fma_rn(ratio, __dadd_rn(fp, fm), base);
+      // `base + ratio * (fp + fm) - (gp + gm)` with base = 2 f0 (1 - ratio): which of the two products the
+      // reference's compiled code fuses depends on ndim (nvcc 12.9, read off the SASS of INTEGRATE_GPU_PHASE1 for
+      // ndim 2..11).  Up to 4 axes the loop over the axes is unrolled before contraction and the base product goes
+      // into the FMA; from 5 axes on base is a rounded loop invariant.  For smooth integrands the difference is far
+      // below the fourth differences, for (bi)linear ones they ARE rounding noise and this decides the axis
+      // (golden xy_2_1e-06, region 9).
+      double t;
+      if constexpr (NDIM <= 4) {
+        t = __fma_rn(__dadd_rn(f0, f0), one_minus_ratio, __dmul_rn(ratio, __dadd_rn(fp, fm)));
+      } else {
+        const double base = __dmul_rn(__dadd_rn(f0, f0), one_minus_ratio);
+        t = __fma_rn(ratio, __dadd_rn(fp, fm), base);
+      }
       const double v = fabs(__dsub_rn(t, __dadd_rn(gp, gm)));
       fd = v > 0.0 ? v : 0.0;
     }
@@ -473,11 +505,13 @@ struct BpLayout {
   static constexpr int kWarpBytes = ((kXBytes + (64 + 3 * NDIM) * 8 + 255) / 256) * 256;
   static constexpr int kMiscDoubles = 2 * PGN_NSETS * PGN_NRULES + 2 * PGN_NCODES;
   static constexpr int kCodesOffset = kWarpsPerBlock * kWarpBytes + kMiscDoubles * 8;
+  // the code table is padded to whole trips of 64 points (the padding holds the centre point's code)
+  static constexpr int kPaddedPoints = ((feval_of(NDIM) + 63) / 64) * 64;
   static constexpr size_t
   bytes()
   {
-    return 256 /* alignment slack */ + kCodesOffset + 16 +
-           static_cast<size_t>(feval_of(NDIM)) * kCodeWords * 4 + feval_of(NDIM);
+    return 256 /* alignment slack */ + kCodesOffset + 16 + static_cast<size_t>(kPaddedPoints) * kCodeWords * 4 +
+           feval_of(NDIM);
   }
 };
 
@@ -488,6 +522,34 @@ lds_f64(uint32_t addr)
   double v;
   asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(IMM) : "memory");
   return v;
+}
+
+// code words of a point: 8 bytes (up to 8 axes) or 16 bytes at a 32-bit shared-memory address
+template <int IMM>
+__device__ __forceinline__ uint2
+lds_u32x2(uint32_t addr)
+{
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(addr), "n"(IMM) : "memory");
+  return v;
+}
+template <int IMM>
+__device__ __forceinline__ uint4
+lds_u32x4(uint32_t addr)
+{
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(addr), "n"(IMM)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ int
+lds_u8(uint32_t addr)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return static_cast<int>(v);
 }
 
 template <int NDIM, int D>
@@ -514,6 +576,57 @@ struct Words4 {
   uint32_t x, y, z, w;
 };
 
+// Cold path of evaluate_kernel_bp for functors with batch_fast: the whole region after the prologue, every point
+// through operator() (the functor's complete code, slow paths included).  Not inlined: its calls into the math
+// library must not constrain the register allocation of the hot loop.
+template <typename F, int NDIM>
+__device__ __noinline__ void
+evaluate_region_exact(F* fptr, const EvalParams& P, size_t reg, int lane, uint32_t lane_codes, uint32_t set_addr,
+                      uint32_t xbase, double* s_f, const double* s_scale, const double* s_norm, double vol,
+                      int max_dim, double jac, double ratio, double one_minus_ratio)
+{
+  using L = BpLayout<NDIM>;
+  constexpr int kFeval = feval_of(NDIM);
+  constexpr int kTrips = (kFeval + 63) / 64;
+  constexpr int kPointBytes = L::kCodeWords * 4;
+  double sa[PGN_NRULES], sb[PGN_NRULES];
+#pragma unroll
+  for (int r = 0; r < PGN_NRULES; ++r)
+    sa[r] = sb[r] = 0.0;
+#pragma unroll 1
+  for (int t = 0; t < kTrips; ++t) {
+#pragma unroll 1
+    for (int m = 0; m < 2; ++m) {
+      const int p = (t << 6) + 32 * m + lane;
+      const uint32_t a = lane_codes + static_cast<uint32_t>(t) * (64u * kPointBytes) + m * (32 * kPointBytes);
+      Words4 cw;
+      if constexpr (L::kCodeWords == 2) {
+        const uint2 v = lds_u32x2<0>(a);
+        cw = Words4{v.x, v.y, 0u, 0u};
+      } else {
+        const uint4 v = lds_u32x4<0>(a);
+        cw = Words4{v.x, v.y, v.z, v.w};
+      }
+      double x[NDIM];
+      BpGather<NDIM, 0>::run(cw, xbase, x);
+      const double fun = __dmul_rn(apply<F, NDIM>(*fptr, x), jac);
+      if (t == 0)
+        s_f[32 * m + lane] = fun;
+      if (p < kFeval) {
+        const double* w = P.wc + lds_u8(set_addr + static_cast<uint32_t>(p)) * PGN_NRULES;
+        double* sum = m == 0 ? sa : sb;
+        sum[0] = __fma_rn(fun, w[0], sum[0]);
+        sum[1] = __fma_rn(fun, w[1], sum[1]);
+        sum[2] = __fma_rn(fun, w[2], sum[2]);
+        sum[3] = __fma_rn(fun, w[3], sum[3]);
+        sum[4] = __fma_rn(fun, w[4], sum[4]);
+      }
+    }
+  }
+  __syncwarp();
+  region_epilogue<NDIM>(P, reg, lane, s_f, s_scale, s_norm, sa, sb, vol, max_dim, ratio, one_minus_ratio);
+}
+
 // The point loop is bound by shared-memory wavefronts (a 64-bit LDS of a warp costs two, a 128-bit
 // one four, whatever the addresses), so everything that is not a genuinely per-lane gather stays
 // out of shared memory:
@@ -539,7 +652,7 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
   double* s_tp = s_norm + PGN_NSETS * PGN_NRULES;
   double* s_tm = s_tp + PGN_NCODES;
   uint32_t* s_codes = reinterpret_cast<uint32_t*>(sm + ((L::kCodesOffset + 15) / 16) * 16);
-  unsigned char* s_set = reinterpret_cast<unsigned char*>(s_codes + feval_of(NDIM) * L::kCodeWords);
+  unsigned char* s_set = reinterpret_cast<unsigned char*>(s_codes + L::kPaddedPoints * L::kCodeWords);
 
   // stage the tables: 4-bit codes widened to one pre-scaled byte per axis
   for (int i = threadIdx.x; i < PGN_NSETS * PGN_NRULES; i += blockDim.x) {
@@ -562,6 +675,8 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
       s_codes[i * L::kCodeWords + k] = words[k];
     s_set[i] = static_cast<unsigned char>(c4 >> 60);
   }
+  for (int i = kFeval * L::kCodeWords + threadIdx.x; i < L::kPaddedPoints * L::kCodeWords; i += blockDim.x)
+    s_codes[i] = 0u;  // code 0 on every axis: the centre
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -575,11 +690,22 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
   double* s_ext = s_up + NDIM;
 
   F* fptr = farg.get();
+  // 32-bit shared-memory addresses of the lane's code word in trip 0 and of the per-point set table
+  uint32_t lane_codes =
+    sm_addr + static_cast<uint32_t>(((L::kCodesOffset + 15) / 16) * 16) + static_cast<uint32_t>(lane) * (L::kCodeWords * 4);
+  uint32_t set_addr =
+    sm_addr + static_cast<uint32_t>(((L::kCodesOffset + 15) / 16) * 16) + static_cast<uint32_t>(L::kPaddedPoints * L::kCodeWords * 4);
+  // opaque to the compiler: under register pressure it would otherwise re-derive these addresses (shared window
+  // base, alignment padding: eight instructions) inside every trip of the point loop instead of keeping a register
+  asm volatile("" : "+r"(lane_codes), "+r"(set_addr));
 
-  constexpr int kFullChunks = kFeval >> 6;
-  // four-point trips only pay for integrands that take them as one batch (otherwise the second pair's
-  // coordinates just add register pressure)
-  constexpr bool kQuadTrips = PGN_EVAL_QUAD != 0 && has_batch<F, NDIM, 4>::value && L::kCodeWords == 2;
+  // Trips: trip t covers points 64t .. 64t+63, the lane's two points are 64t+lane (chain A = reference thread
+  // `lane`) and 64t+32+lane (chain B = thread lane+32).  The code table is padded to a whole number of trips
+  // (with the centre point), so a gather never needs a bounds check; results of non-existent points are dropped
+  // by predication.
+  constexpr int kTrips = (kFeval + 63) / 64;
+  constexpr int kMiddle = kTrips >= 2 ? kTrips - 2 : 0;       // trips 1 .. kTrips-2: all 64 points exist
+  constexpr bool kFast = has_batch_fast<F, NDIM, 2>::value;   // straight-line values + exact fallback per region
   const double jac = P.jacobian;
   const double ratio = P.ratio;
   const double one_minus_ratio = __dsub_rn(1.0, ratio);
@@ -596,55 +722,34 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
 #pragma unroll
     for (int r = 0; r < PGN_NRULES; ++r)
       sa[r] = sb[r] = 0.0;
+    bool exact = true;  // kFast: no lane needed the functor's slow path so far
 
-    // f(x_p) * Jacobian of the lane's point p
-    auto point_value = [&](int p) -> double {
-      Words4 cw;
+    // coordinates of the lane's two points of trip t (one address computation for both code words)
+    auto gather = [&](double (&x)[2][NDIM], int t) {
+      constexpr int kPointBytes = L::kCodeWords * 4;
+      const uint32_t a = lane_codes + static_cast<uint32_t>(t) * (64u * kPointBytes);
+      Words4 ca, cb;
       if constexpr (L::kCodeWords == 2) {
-        const uint2 v = *reinterpret_cast<const uint2*>(s_codes + 2 * p);
-        cw.x = v.x;
-        cw.y = v.y;
-        cw.z = cw.w = 0u;
+        const uint2 va = lds_u32x2<0>(a), vb = lds_u32x2<32 * kPointBytes>(a);
+        ca = Words4{va.x, va.y, 0u, 0u};
+        cb = Words4{vb.x, vb.y, 0u, 0u};
       } else {
-        const uint4 v = *reinterpret_cast<const uint4*>(s_codes + 4 * p);
-        cw.x = v.x;
-        cw.y = v.y;
-        cw.z = v.z;
-        cw.w = v.w;
+        const uint4 va = lds_u32x4<0>(a), vb = lds_u32x4<32 * kPointBytes>(a);
+        ca = Words4{va.x, va.y, va.z, va.w};
+        cb = Words4{vb.x, vb.y, vb.z, vb.w};
       }
-      double x[NDIM];
-      BpGather<NDIM, 0>::run(cw, xbase, x);
-      const double fv = apply<F, NDIM>(*fptr, x);
-      return __dmul_rn(fv, jac);
+      BpGather<NDIM, 0>::run(ca, xbase, x[0]);
+      BpGather<NDIM, 0>::run(cb, xbase, x[1]);
     };
-    // the same for M points at once: p[m] are the lane's points, f[m] = f(x_p[m]) * Jacobian
-    auto point_values = [&](auto m_tag, const int (&p)[decltype(m_tag)::value],
-                            double (&f)[decltype(m_tag)::value]) {
-      constexpr int M = decltype(m_tag)::value;
-      if constexpr (has_batch<F, NDIM, M>::value) {
-        double x[M][NDIM];
-#pragma unroll
-        for (int m = 0; m < M; ++m) {
-          Words4 cw;
-          if constexpr (L::kCodeWords == 2) {
-            const uint2 v = *reinterpret_cast<const uint2*>(s_codes + 2 * p[m]);
-            cw = Words4{v.x, v.y, 0u, 0u};
-          } else {
-            const uint4 v = *reinterpret_cast<const uint4*>(s_codes + 4 * p[m]);
-            cw = Words4{v.x, v.y, v.z, v.w};
-          }
-          BpGather<NDIM, 0>::run(cw, xbase, x[m]);
-        }
-        double fv[M];
-        BatchCall<F, NDIM, M>::run(fptr, x, fv);
-#pragma unroll
-        for (int m = 0; m < M; ++m)
-          f[m] = __dmul_rn(fv[m], jac);
-      } else {
-#pragma unroll
-        for (int m = 0; m < M; ++m)
-          f[m] = point_value(p[m]);
-      }
+    // f(x) * Jacobian of both points
+    auto values = [&](const double (&x)[2][NDIM], double (&f)[2]) {
+      double fv[2];
+      if constexpr (kFast)
+        exact = static_cast<const F*>(fptr)->template batch_fast<2>(x, fv) && exact;
+      else
+        BatchCall<F, NDIM, 2>::run(fptr, x, fv);
+      f[0] = __dmul_rn(fv[0], jac);
+      f[1] = __dmul_rn(fv[1], jac);
     };
     auto accumulate = [&](double (&sum)[PGN_NRULES], double fun, const double* w) {
       sum[0] = __fma_rn(fun, w[0], sum[0]);
@@ -653,99 +758,105 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
       sum[3] = __fma_rn(fun, w[3], sum[3]);
       sum[4] = __fma_rn(fun, w[4], sum[4]);
     };
-    // generic path: q = first point of the 32-point half-chunk of p (warp uniform); the set is
-    // uniform for most half-chunks, otherwise looked up per lane
-    auto eval_point = [&](int q, int p, double (&sum)[PGN_NRULES], bool keep_f, int slot) {
-      const double fun = point_value(p);
-      if (keep_f)
-        s_f[slot] = fun;
-      int set = P.half_set[q >> 5];
-      if (set == 0xFF)
-        set = s_set[p];
-#ifdef PGN_DEBUG_UNIT_WEIGHTS  // timing experiment only (results are wrong): no weight fetch at all
-      const double w[5] = {1.0, 2.0, 3.0, 4.0, 5.0};
-      (void)set;
-#else
-      const double* w = P.wc + set * PGN_NRULES;
-#endif
-      accumulate(sum, fun, w);
-    };
-
     // per-lane rule weights of point p in the half-chunk starting at q (uniform for most half-chunks)
     auto lane_weights = [&](int q, int p) -> const double* {
       int set = P.half_set[q >> 5];
       if (set == 0xFF)
-        set = s_set[p];
+        set = lds_u8(set_addr + static_cast<uint32_t>(p < kFeval ? p : 0));
       return P.wc + set * PGN_NRULES;
     };
-    // chunk 0 keeps its function values for the fourth differences (Sample.cuh:176-219)
-    if constexpr (kFeval >= 64) {
-      const int p[2] = {lane, lane + 32};
+    // a trip whose points may belong to different generator sets and may not all exist (first, last)
+    auto ragged_trip = [&](const double (&x)[2][NDIM], int t, bool keep_f) {
+      const int pa = (t << 6) + lane, pb = pa + 32;
       double f[2];
-      point_values(std::integral_constant<int, 2>{}, p, f);
-      s_f[lane] = f[0];
-      s_f[lane + 32] = f[1];
-      accumulate(sa, f[0], lane_weights(0, lane));
-      accumulate(sb, f[1], lane_weights(32, lane + 32));
-    } else {
-      eval_point(0, lane, sa, true, lane);
-      if (lane + 32 < kFeval)
-        eval_point(32, lane + 32, sb, true, lane + 32);
-    }
-    // full chunks: both emulated threads of every lane are busy.  Runs of chunks whose 64 points all
-    // belong to one generator set (most of them) keep the five weights in (uniform) registers and take
-    // two chunks -- four points per lane -- per trip while the run lasts.
-    {
-      int k = 1;
-#pragma unroll 1
-      while (k < kFullChunks) {
-        const int st = P.chunk_set[k];
-        if (st != 0xFF) {
-          const double w[PGN_NRULES] = {P.wc[st * PGN_NRULES + 0], P.wc[st * PGN_NRULES + 1],
-                                        P.wc[st * PGN_NRULES + 2], P.wc[st * PGN_NRULES + 3],
-                                        P.wc[st * PGN_NRULES + 4]};
-#pragma unroll 1
-          do {
-            const int q = k << 6;
-            if (kQuadTrips && k + 1 < kFullChunks && P.chunk_set[k + 1] == st) {
-              const int p[4] = {q + lane, q + 32 + lane, q + 64 + lane, q + 96 + lane};
-              double f[4];
-              point_values(std::integral_constant<int, 4>{}, p, f);
-              accumulate(sa, f[0], w);
-              accumulate(sb, f[1], w);
-              accumulate(sa, f[2], w);
-              accumulate(sb, f[3], w);
-              k += 2;
-            } else {
-              const int p[2] = {q + lane, q + 32 + lane};
-              double f[2];
-              point_values(std::integral_constant<int, 2>{}, p, f);
-              accumulate(sa, f[0], w);
-              accumulate(sb, f[1], w);
-              ++k;
-            }
-          } while (k < kFullChunks && P.chunk_set[k] == st);
-        } else {
-          const int q = k << 6;
-          const int p[2] = {q + lane, q + 32 + lane};
-          double f[2];
-          point_values(std::integral_constant<int, 2>{}, p, f);
-          accumulate(sa, f[0], lane_weights(q, p[0]));
-          accumulate(sb, f[1], lane_weights(q + 32, p[1]));
-          ++k;
+      values(x, f);
+      if (keep_f) {
+        s_f[lane] = f[0];
+        s_f[lane + 32] = f[1];
+      }
+      if (pa < kFeval)
+        accumulate(sa, f[0], lane_weights(t << 6, pa));
+      if (pb < kFeval)
+        accumulate(sb, f[1], lane_weights((t << 6) + 32, pb));
+    };
+    // rule weights of the current uniform run (registers), reloaded when the generator set changes
+    double w[PGN_NRULES] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    int cur_set = -1;
+    auto middle_trip = [&](const double (&x)[2][NDIM], int t) {
+      double f[2];
+      values(x, f);
+      const int st = P.chunk_set[t];
+      if (st != 0xFF) {
+        if (st != cur_set) {
+          cur_set = st;
+#pragma unroll
+          for (int r = 0; r < PGN_NRULES; ++r)
+            w[r] = P.wc[st * PGN_NRULES + r];
         }
+        accumulate(sa, f[0], w);
+        accumulate(sb, f[1], w);
+      } else {
+        const int pa = (t << 6) + lane;
+        accumulate(sa, f[0], lane_weights(t << 6, pa));
+        accumulate(sb, f[1], lane_weights((t << 6) + 32, pa + 32));
+      }
+    };
+
+#if PGN_EVAL_PIPELINE
+    // Software pipeline: the 2 + 2*NDIM shared-memory loads of trip t+1 are issued before the arithmetic of
+    // trip t, into a second coordinate buffer.  Measured on B200 (profiles/r02_evalbench_pipeline.jsonl): no gain
+    // for the oscillatory family, 5-19 % slower for the register-hungry pow families -- with 4-5 warps per
+    // scheduler the loads of one warp already overlap the arithmetic of the others.  Kept as an option.
+    double x0[2][NDIM], x1[2][NDIM];
+    gather(x0, 0);
+    if constexpr (kTrips >= 2)
+      gather(x1, 1);
+    ragged_trip(x0, 0, true);
+    if constexpr (kTrips >= 2) {
+      int t = 1;
+#pragma unroll 1
+      for (; t + 1 <= kMiddle; t += 2) {
+        gather(x0, t + 1);
+        middle_trip(x1, t);
+        gather(x1, t + 2);
+        middle_trip(x0, t + 1);
+      }
+      if constexpr (kMiddle & 1) {  // t == kMiddle, odd: its coordinates are in x1
+        gather(x0, kMiddle + 1);
+        middle_trip(x1, kMiddle);
+      }
+      if constexpr (((kTrips - 1) & 1) != 0)
+        ragged_trip(x1, kTrips - 1, false);
+      else
+        ragged_trip(x0, kTrips - 1, false);
+    }
+#else
+    {
+      double x[2][NDIM];
+      // trip 0 keeps its function values for the fourth differences (Sample.cuh:176-219)
+      gather(x, 0);
+      ragged_trip(x, 0, true);
+      if constexpr (kTrips >= 2) {
+#pragma unroll 1
+        for (int t = 1; t <= kMiddle; ++t) {
+          gather(x, t);
+          middle_trip(x, t);
+        }
+        // last trip (Sample.cuh:238-252): only some of its points exist
+        gather(x, kTrips - 1);
+        ragged_trip(x, kTrips - 1, false);
       }
     }
-    // ragged tail (Sample.cuh:238-252)
-    if (kFullChunks >= 1) {
-      constexpr int q = kFullChunks << 6;
-      const int p = q + lane;
-      if (p < kFeval)
-        eval_point(q, p, sa, false, 0);
-      if (p + 32 < kFeval)
-        eval_point(q + 32, p + 32, sb, false, 0);
-    }
+#endif
     __syncwarp();
+    if constexpr (kFast) {
+      if (!__all_sync(0xffffffffu, exact)) {
+        // some lane's argument needs the functor's slow path: redo the region with operator() (cold)
+        evaluate_region_exact<F, NDIM>(fptr, P, reg, lane, lane_codes, set_addr, xbase, s_f, s_scale, s_norm, vol,
+                                       max_dim, jac, ratio, one_minus_ratio);
+        continue;
+      }
+    }
     region_epilogue<NDIM>(P, reg, lane, s_f, s_scale, s_norm, sa, sb, vol, max_dim, ratio,
                           one_minus_ratio);
   }

@@ -32,11 +32,11 @@
 #ifndef PGN_GENZ_FAST_POW
 #define PGN_GENZ_FAST_POW 1
 #endif
-// PGN_GENZ_FAST_EXP (default 0): exp() of the Gaussian, C0 and discontinuous families through fastmath::exp_pinned
-// (bit-identical to exp() on the GPU; not the default until the kernels are timed and the parity cases run with it:
-// tools/gpu_exp_check.sh)
+// PGN_GENZ_FAST_EXP (default 1): exp() of the Gaussian, C0 and discontinuous families through fastmath::exp_pinned
+// (bit-identical to exp() on the GPU, tests/cpp/test_fastmath.cu; the C0 / discontinuous / Gaussian trajectories were
+// re-run against the reference's goldens with it in round 2: profiles/r02_pytest_gpu_sessionC.txt; F_5_10D +8 %)
 #ifndef PGN_GENZ_FAST_EXP
-#define PGN_GENZ_FAST_EXP 0
+#define PGN_GENZ_FAST_EXP 1
 #endif
 #if PGN_GENZ_FAST_EXP && !defined(PGN_GENZ_LIBRARY_MATH)
 #define PGN_GENZ_EXP(x) ::pagani_b200::fastmath::exp_pinned(x)
@@ -104,6 +104,24 @@ struct Oscillatory {
         s[m] = s[m] + static_cast<double>(k + 1) * x[m][k];
     }
     ::pagani_b200::fastmath::cos_pinned_n<M>(s, f);
+  }
+  // straight-line form (evaluate.cuh: has_batch_fast): false when an argument needs cos()'s slow path
+  template <int M>
+  __device__ bool
+  batch_fast(const double (&x)[M][N], double (&f)[M]) const
+  {
+    bool ok = true;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      double s = x[m][0];
+#pragma unroll
+      for (int k = 1; k < N; ++k)
+        s = s + static_cast<double>(k + 1) * x[m][k];
+      bool okc;
+      f[m] = ::pagani_b200::fastmath::cos_fast(s, &okc);
+      ok = ok && okc;
+    }
+    return ok;
   }
 #endif
 };
@@ -194,6 +212,34 @@ struct Gaussian {
 #endif
     return PGN_GENZ_EXP(-1.0 * s);
   }
+#if defined(__CUDACC__) && PGN_GENZ_FAST_POW && !defined(PGN_GENZ_LIBRARY_MATH) && !defined(PGN_GENZ_NO_BATCH)
+  // call-free form (evaluate.cuh: has_batch_fast): the library's pow(x, 2.) operation sequence without its
+  // special-case branch (the only CALL of this functor); false when it would have been taken.  exp() is inline code
+  // in either form.
+  template <int M>
+  __device__ bool
+  batch_fast(const double (&x)[M][N], double (&f)[M]) const
+  {
+    const double beta = .5;
+    bool ok = true;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      double sq[N];
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        bool okk;
+        sq[k] = ::pagani_b200::fastmath::pow2_fast(x[m][k] - beta, &okk);
+        ok = ok && okk;
+      }
+      double s = pow(25., 2.) * sq[0];
+#pragma unroll
+      for (int k = 1; k < N; ++k)
+        s = s + pow(25., 2.) * sq[k];
+      f[m] = PGN_GENZ_EXP(-1.0 * s);
+    }
+    return ok;
+  }
+#endif
 };
 
 // F_5: exp(-10 sum_k |x_k - .5|)
@@ -319,40 +365,8 @@ struct Discontinuous {
     }
     return PGN_GENZ_EXP(s);
   }
-#if defined(__CUDACC__) && PGN_GENZ_FAST_EXP && !defined(PGN_GENZ_LIBRARY_MATH) && !defined(PGN_GENZ_NO_BATCH)
-  // M points at once: exponent and exp for every point (harmless for the ones outside), then the zero
-  template <int M>
-  __device__ void
-  batch(const double (&x)[M][N], double (&f)[M]) const
-  {
-    double s[M];
-    bool outside[M];
-#pragma unroll
-    for (int m = 0; m < M; ++m) {
-      outside[m] = false;
-#pragma unroll
-      for (int k = 0; k < N; ++k)
-        outside[m] = outside[m] || (x[m][k] > Spec::beta(k));
-      if (Spec::descending) {
-        s[m] = mul_rn(Spec::alpha(N - 1), x[m][N - 1]);
-#pragma unroll
-        for (int k = N - 2; k >= 0; --k)
-          s[m] = fma_rn(Spec::alpha(k), x[m][k], s[m]);
-      } else {
-        s[m] = mul_rn(Spec::alpha(1), x[m][1]);
-        s[m] = fma_rn(Spec::alpha(0), x[m][0], s[m]);
-#pragma unroll
-        for (int k = 2; k < N; ++k)
-          s[m] = fma_rn(Spec::alpha(k), x[m][k], s[m]);
-      }
-    }
-    double e[M];
-    ::pagani_b200::fastmath::exp_pinned_n<M>(s, e);
-#pragma unroll
-    for (int m = 0; m < M; ++m)
-      f[m] = outside[m] ? 0. : e[m];
-  }
-#endif
+  // (no batch form: most points of this family lie outside the support, and operator() skips their exp entirely --
+  // measured 3.4e11 evaluations/s at 10-D against 2.4e11 with an unconditional batched exp, profiles/r02_evalbench_c.jsonl)
 };
 
 }  // namespace genz

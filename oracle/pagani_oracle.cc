@@ -142,7 +142,11 @@ evaluate_region(const Rule& R, Integrand f, const double* left, const double* le
     for (int d = 0; d < nd; ++d) {
       const double fp = sdata[1 + 2 * d], fm = sdata[2 + 2 * d];
       const double gp = sdata[1 + 2 * d + 2 * nd], gm = sdata[2 + 2 * d + 2 * nd];
-      const double fourth = std::fabs(std::fma(ratio, fp + fm, base) - (gp + gm));
+      // `base + ratio * (fp + fm) - ...`: which product nvcc 12.9 fuses depends on ndim.  Up to 4 axes the loop is
+      // unrolled before contraction and the base product goes into the FMA (the other one is rounded); from 5 axes
+      // on base is a rounded loop invariant (read off the reference kernels' SASS for ndim 2..11).
+      const double t = nd <= 4 ? std::fma(sdata[0] + sdata[0], 1 - ratio, ratio * (fp + fm)) : std::fma(ratio, fp + fm, base);
+      const double fourth = std::fabs(t - (gp + gm));
       if (fourth > maxdiff) {
         maxdiff = fourth;
         bisect = d;

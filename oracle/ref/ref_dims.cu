@@ -23,6 +23,18 @@ struct RefXY2 {
 };
 REF_REGISTER(const_2, RefConst2, 2)
 REF_REGISTER(xy_2, RefXY2, 2)
+#elif REF_NDIM == 3
+// products of the coordinates at 3 and 4 axes: multilinear, so the fourth differences are pure rounding noise and the
+// split axes pin the reference's machine code for these dimensions (its contraction choices depend on ndim)
+struct RefXY3 {
+  __device__ __host__ double operator()(double x, double y, double z) { return x * y * z; }
+};
+REF_REGISTER(xy_3, RefXY3, 3)
+#elif REF_NDIM == 4
+struct RefXY4 {
+  __device__ __host__ double operator()(double x, double y, double z, double w) { return x * y * z * w; }
+};
+REF_REGISTER(xy_4, RefXY4, 4)
 #elif REF_NDIM == 5
 REF_REGISTER(f1_5, F_1_5D, 5)
 REF_REGISTER(f2_5, F_2_5D, 5)

@@ -34,7 +34,8 @@ class _Workspace:
         for it, (n, act) in enumerate([(256, 256), (512, 512), (1024, 492)]):
             self._tr.append({"iteration": it, "nregions": n, "nregions_global": n, "nactive": act, "eval_ms": 0.5 * (it + 1),
                              "classify_ms": 0.01, "heuristic_ms": 0.02 * it, "split_ms": 0.03, "heuristic_probes": it,
-                             "heuristic_ran": int(it == 2)})
+                             "heuristic_ran": int(it == 2), "budget_overflow": 0, "iter_estimate": 3.4e-5,
+                             "iter_errorest": 1e-7})
         return _Result(sum(t["nregions"] for t in self._tr) * 1105, 1792, 0)
 
     def trace(self):
@@ -127,6 +128,13 @@ def test_bench_line_carries_every_contract_key(bench, monkeypatch):
     # evaluations of one step / device time of the timed steps
     evals_per_step = 6 * (256 + 512 + 1024) * 1105
     assert d["value"] == pytest.approx(evals_per_step * 2 / 12.5e-3)
+    # trajectory parity against the committed goldens is part of the line (the stand-in engine does not follow them)
+    assert d["parity_ok"] is False and len(d["parity"]["cases"]) == 6
+    assert all(c["case"].startswith("f1_8_") and c["ok"] is False for c in d["parity"]["cases"])
+    # BASELINE configs 3-5 and the native-mode tolerance ladder ride along as side records
+    assert [c["family"] for c in d["configs"]] == [2, 5, 6, 4] and all("parity" in c and "ours" in c for c in d["configs"])
+    assert d["native_ladder"]["steps"] and d["native_ladder"]["steps"][0]["epsrel"] == 1e-3
+    assert d["roofline"]["fp64_pipe_pct"] > 0 and d["roofline"]["frac_executed"] > 0
     hbm = d["roofline_hbm"]
     assert "error" not in hbm and hbm["regions"] == 1024 and hbm["largest_all_active_iteration"]["regions"] == 512
 

@@ -78,7 +78,7 @@ mix(double* out, long long* cycles, int iters, double x, double y)
     f[c] = threadIdx.x + c;
     d[c] = threadIdx.x * 0.25 + c;
   }
-  const unsigned saddr = static_cast<unsigned>(__cvta_generic_to_shared(s_tab)) + (threadIdx.x & 7) * 8;
+  const unsigned saddr = static_cast<unsigned>(__cvta_generic_to_shared(s_tab)) + (threadIdx.x & 3) * 16;
   __syncthreads();
   const long long t0 = clock64();
   for (int i = 0; i < iters; ++i) {

@@ -28,6 +28,8 @@ CASES = [
     # the other families / dimensions
     (4, 8, 1e-4, 0), (5, 8, 1e-3, 1024), (6, 6, 1e-3, 1024), (2, 6, 1e-3, 512), (2, 6, 1e-5, 0), (3, 8, 1e-3, 1024),
     (1, 5, 1e-6, 512), (3, 5, 1e-5, 512), (4, 7, 1e-4, 0), (6, 7, 1e-3, 512), (0, 2, 1e-3, 1024), (7, 2, 1e-6, 1024),
+    # multilinear integrands at 3 and 4 axes: split axes decided by rounding noise (the reference's contraction choices)
+    (7, 3, 1e-8, 1024), (7, 4, 1e-8, 1024),
 ]
 NAMES = {0: "const", 7: "xy"}
 
