@@ -237,8 +237,15 @@ super_tiles_for(unsigned int tiles)
   return (tiles + kSuper - 1) / kSuper;
 }
 
+// launch-bound / pipeline-depth knobs of k_classify (tools/gpu_sessions sweep them through alternative builds)
+#ifndef PGN_CLASSIFY_MINBLOCKS
+#define PGN_CLASSIFY_MINBLOCKS 3
+#endif
+#ifndef PGN_CLASSIFY_DEPTH
+#define PGN_CLASSIFY_DEPTH 2
+#endif
 template <bool REFINE>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, PGN_CLASSIFY_MINBLOCKS)
 k_classify(const double* __restrict__ est, const double* __restrict__ err_raw,
            const double* __restrict__ parent_est, double* __restrict__ err_out,
            uint8_t* __restrict__ active, size_t n, double epsrel, int relerr_classification,
@@ -262,71 +269,77 @@ k_classify(const double* __restrict__ est, const double* __restrict__ err_raw,
   __syncthreads();
   dev::Acc a;
   dev::acc_zero(a);
-#pragma unroll 1
-  for (int k = 0; k < kSuper; ++k) {
-    const unsigned int tile = sup * kSuper + k;
-    if (tile >= tiles)
-      break;  // uniform over the block
-    const size_t base = static_cast<size_t>(tile) * kTile;
-    // all loads of the four rounds first (clamped indices, so they are unconditional): 20 independent
-    // loads in flight per thread instead of four exposed round trips
-    double v_est[kRounds], v_err[kRounds], v_sib_est[kRounds], v_sib_err[kRounds], v_par[kRounds];
+  // The 16 rounds of a super-tile (256 regions each) run as a software pipeline of depth kDepth: the five loads of
+  // round r + kDepth are issued before the arithmetic of round r, so a thread always has 5 * kDepth loads in flight
+  // while it computes (one correctly rounded FP64 division and seven accumulations per region: about as many FP64
+  // pipe cycles as the 29 bytes cost in HBM time -- a load-everything-then-compute loop pays both in turn).
+  constexpr int kSteps = kSuper * kRounds;
+  constexpr int kDepth = PGN_CLASSIFY_DEPTH;
+  const size_t sbase = static_cast<size_t>(sup) * kSuper * kTile;
+  struct Stage {
+    double est, err, sib_est, sib_err, par;
+  };
+  Stage st[kDepth];
+  auto load = [&](int step, Stage& s) {
+    size_t i = sbase + static_cast<size_t>(step) * kBlock + threadIdx.x;
+    i = i < n ? i : n - 1;  // clamped: the loads are unconditional
+    s.est = est[i];
+    s.err = err_raw[i];
+    if constexpr (REFINE) {
+      const bool right = (i + i) >= n;
+      const size_t sib = right ? i - half : i + half;
+      const size_t par = right ? i - half : i;
+      s.sib_est = est[sib];
+      s.sib_err = err_raw[sib];
+      s.par = parent_est[par];
+    }
+  };
 #pragma unroll
-    for (int q = 0; q < kRounds; ++q) {
-      size_t i = base + static_cast<size_t>(q) * kBlock + threadIdx.x;
-      i = i < n ? i : n - 1;
-      v_est[q] = est[i];
-      v_err[q] = err_raw[i];
+  for (int d = 0; d < kDepth; ++d)
+    load(d, st[d]);
+  int my_active = 0;
+#pragma unroll
+  for (int step = 0; step < kSteps; ++step) {
+    const Stage cur = st[step % kDepth];
+    if (step + kDepth < kSteps)
+      load(step + kDepth, st[step % kDepth]);
+    const size_t i = sbase + static_cast<size_t>(step) * kBlock + threadIdx.x;
+    if (i < n) {
+      const double self_est = cur.est;
+      double e = cur.err;
+      double flag = 1.0;
       if constexpr (REFINE) {
-        const bool right = (i + i) >= n;
-        const size_t sib = right ? i - half : i + half;
-        const size_t par = right ? i - half : i;
-        v_sib_est[q] = est[sib];
-        v_sib_err[q] = err_raw[sib];
-        v_par[q] = parent_est[par];
-      }
-    }
-    int my_active = 0;
-#pragma unroll
-    for (int q = 0; q < kRounds; ++q) {
-      const size_t i = base + static_cast<size_t>(q) * kBlock + threadIdx.x;
-      if (i < n) {
-        const double self_est = v_est[q];
-        double e = v_err[q];
-        double flag = 1.0;
-        if constexpr (REFINE) {
-          const double sib_est = v_sib_est[q];
-          const double sib_err = v_sib_err[q];
-          const double par_est = v_par[q];
-          // Phases.cuh:251-261 with the rounding sequence of the reference's machine code
-          const double diff = fabs(__dmul_rn(__dsub_rn(__dadd_rn(self_est, sib_est), par_est), 0.25));
-          const double both = __dadd_rn(e, sib_err);
-          if (both > 0.0) {
-            const double c = __dadd_rn(__ddiv_rn(__dadd_rn(diff, diff), both), 1.0);
-            e = __dmul_rn(e, c);
-          }
-          e = __dadd_rn(diff, e);
-          err_out[i] = e;
-          if (relerr_classification) {
-            const double tol = fmax(__dmul_rn(epsrel, fabs(self_est)), 1e-200);
-            flag = (e < tol) ? 0.0 : 1.0;
-          }
+        // Phases.cuh:251-261 with the rounding sequence of the reference's machine code
+        const double diff = fabs(__dmul_rn(__dsub_rn(__dadd_rn(self_est, cur.sib_est), cur.par), 0.25));
+        const double both = __dadd_rn(e, cur.sib_err);
+        if (both > 0.0) {
+          const double c = __dadd_rn(__ddiv_rn(__dadd_rn(diff, diff), both), 1.0);
+          e = __dmul_rn(e, c);
         }
-        active[i] = flag != 0.0 ? 1 : 0;
-        my_active += flag != 0.0 ? 1 : 0;
-        a.v[kSumEst] += self_est;
-        a.v[kSumErr] += e;
-        a.v[kSumActEst] += flag * self_est;  // thrust::inner_product(flags, estimates)
-        a.v[kSumActErr] += flag * e;
-        a.v[kNumActive] += flag;
-        a.mn = fmin(a.mn, e);
-        a.mx = fmax(a.mx, e);
+        e = __dadd_rn(diff, e);
+        err_out[i] = e;
+        if (relerr_classification) {
+          const double tol = fmax(__dmul_rn(epsrel, fabs(self_est)), 1e-200);
+          flag = (e < tol) ? 0.0 : 1.0;
+        }
       }
+      active[i] = flag != 0.0 ? 1 : 0;
+      my_active += flag != 0.0 ? 1 : 0;
+      a.v[kSumEst] += self_est;
+      a.v[kSumErr] += e;
+      a.v[kSumActEst] += flag * self_est;  // thrust::inner_product(flags, estimates)
+      a.v[kSumActErr] += flag * e;
+      a.v[kNumActive] += flag;
+      a.mn = fmin(a.mn, e);
+      a.mx = fmax(a.mx, e);
     }
-    // active regions of this tile: warp sums into a shared counter (integers: order does not matter)
-    const int warp_active = __reduce_add_sync(0xffffffffu, my_active);
-    if ((threadIdx.x & 31) == 0 && warp_active)
-      atomicAdd(&s_tile_active[k], static_cast<unsigned int>(warp_active));
+    if ((step % kRounds) == kRounds - 1) {
+      // active regions of the tile just finished: warp sums into a shared counter (integers: order does not matter)
+      const int warp_active = __reduce_add_sync(0xffffffffu, my_active);
+      if ((threadIdx.x & 31) == 0 && warp_active)
+        atomicAdd(&s_tile_active[step / kRounds], static_cast<unsigned int>(warp_active));
+      my_active = 0;
+    }
   }
   __syncthreads();
   if (threadIdx.x < kSuper && sup * kSuper + threadIdx.x < tiles)

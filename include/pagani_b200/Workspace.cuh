@@ -8,7 +8,7 @@
 //           (reference cuda/pagani/quad/GPUquad/Workspace.cuh:23-71, 148-358, 361-494)
 //           numint::integration_result   (common/integration_result.hh:11-21)
 //           quad::Volume<T,NDIM>         (common/cuda/Volume.cuh:13-52)
-//           Sub_regions<T,ndim>          (GPUquad/Sub_regions.cuh:38-258; host-visible subset)
+//           Sub_regions<T,ndim> and the other stage-level classes: stages.cuh
 // The integrand is any copyable functor with a __device__ double operator()(double x ndim); it is
 // compiled into the evaluation kernel of evaluate.cuh, everything else runs behind the C ABI.
 // Errors: CUDA failures abort with a message like the reference's CudaCheckError
@@ -16,124 +16,10 @@
 #ifndef PAGANI_B200_WORKSPACE_CUH
 #define PAGANI_B200_WORKSPACE_CUH
 
-#include <array>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <new>
-#include <ostream>
+#include <fstream>
 #include <string>
-#include <vector>
 
-#include "../pagani_b200.h"
-#include "evaluate.cuh"
-
-namespace numint {
-  struct integration_result {
-    double estimate = 0.;
-    double errorest = 0.;
-    size_t neval = 0;
-    size_t nregions = 0;
-    size_t nFinishedRegions = 0;
-    int status = -1;
-    int lastPhase = -1;
-    double chi_sq = 0.;
-    size_t iters = 0;
-  };
-  inline std::ostream&
-  operator<<(std::ostream& os, integration_result const& res)
-  {
-    os << res.estimate << "," << res.errorest << "," << res.nregions << "," << res.chi_sq << ","
-       << res.status;
-    return os;
-  }
-}
-
-namespace quad {
-  template <typename T, int NDIM>
-  struct Volume {
-    T lows[NDIM] = {0.0};
-    T highs[NDIM];
-    Volume()
-    {
-      for (T& x : highs)
-        x = 1.0;
-    }
-    Volume(std::array<T, NDIM> l, std::array<T, NDIM> h)
-    {
-      std::memcpy(lows, l.data(), NDIM * sizeof(T));
-      std::memcpy(highs, h.data(), NDIM * sizeof(T));
-    }
-    Volume(T const* l, T const* h)
-    {
-      std::memcpy(lows, l, NDIM * sizeof(T));
-      std::memcpy(highs, h, NDIM * sizeof(T));
-    }
-    Volume(T l, T h)
-    {
-      for (int d = 0; d < NDIM; ++d) {
-        lows[d] = l;
-        highs[d] = h;
-      }
-    }
-  };
-}
-
-namespace pagani_b200 {
-  inline void
-  check(int rc, const char* what)
-  {
-    if (rc == PGN_OK)
-      return;
-    if (rc == PGN_ERR_NOMEM)
-      throw std::bad_alloc();
-    std::fprintf(stderr, "pagani_b200: %s failed (%d): %s\n", what, rc, pgn_last_error());
-    std::abort();
-  }
-}
-
-// The caller-visible region list.  The device copy lives inside the Workspace's engine context;
-// this object carries what the caller specified (a uniform grid or explicit host arrays) and, after
-// integrate(), the size of the list the run ended with.
-template <typename T, size_t ndim>
-struct Sub_regions {
-  Sub_regions() {}
-  explicit Sub_regions(const size_t partitions_per_axis) { uniform_split(partitions_per_axis); }
-
-  void
-  uniform_split(size_t numOfDivisionPerRegionPerDimension)
-  {
-    partitions = numOfDivisionPerRegionPerDimension;
-    size = 1;
-    for (size_t d = 0; d < ndim; ++d)
-      size *= partitions;
-    LeftCoord.clear();
-    Length.clear();
-  }
-
-  // explicit list, SoA [dim * n + i] exactly like dLeftCoord / dLength of the reference
-  void
-  set_host(const T* left, const T* length, size_t n)
-  {
-    partitions = 0;
-    size = n;
-    LeftCoord.assign(left, left + n * ndim);
-    Length.assign(length, length + n * ndim);
-  }
-
-  T
-  compute_region_volume(size_t const regionID) const
-  {
-    T reg_vol = 1.;
-    for (size_t dim = 0; dim < ndim; dim++)
-      reg_vol *= Length[size * dim + regionID];
-    return reg_vol;
-  }
-
-  std::vector<T> LeftCoord, Length;  // host copies, filled by Workspace::refresh_host
-  size_t partitions = 0;
-  size_t size = 0;
-};
+#include "stages.cuh"
 
 template <typename T, size_t ndim, int debug = 0, bool use_custom = false, bool collect_mult_runs = false>
 class Workspace {
@@ -159,20 +45,17 @@ public:
             const std::string& optional = "default")
   {
     (void)optional;
-    if (subregions.partitions > 0)
-      pagani_b200::check(pgn_regions_init_uniform(ctx_, static_cast<int>(subregions.partitions)),
-                         "pgn_regions_init_uniform");
-    else
-      pagani_b200::check(pgn_regions_import(ctx_, subregions.LeftCoord.data(), subregions.Length.data(),
-                                            subregions.size),
-                         "pgn_regions_import");
-    numint::integration_result res = run(integrand, epsrel, epsabs, vol, relerr_classification, true);
+    // the caller's device list is copied into the engine's arena; afterwards the caller's object is re-pointed at a
+    // copy of the list the run ended with (the reference frees and replaces its arrays every iteration,
+    // Workspace.cuh:148-358)
+    pagani_b200::check(pgn_regions_import_device(ctx_, subregions.dLeftCoord, subregions.dLength, subregions.size),
+                       "pgn_regions_import_device");
+    numint::integration_result res = run(integrand, epsrel, epsabs, vol, relerr_classification, true, optional);
     size_t n = 0;
     pgn_regions_count(ctx_, &n);
-    subregions.size = n;  // the reference leaves the caller's list replaced by the final one
-    subregions.partitions = 0;
-    subregions.LeftCoord.clear();
-    subregions.Length.clear();
+    subregions.device_init(n);
+    pagani_b200::check(pgn_regions_export_device(ctx_, subregions.dLeftCoord, subregions.dLength, n, &n),
+                       "pgn_regions_export_device");
     return res;
   }
 
@@ -184,27 +67,13 @@ public:
     return run(integrand, epsrel, epsabs, vol, relerr_classification, false);
   }
 
-  // Sub_regions::refresh_host_device (Sub_regions.cuh:82-87): copy the engine's current list back
-  void
-  refresh_host(Sub_regions<T, ndim>& subregions)
-  {
-    size_t n = 0;
-    pgn_regions_count(ctx_, &n);
-    subregions.LeftCoord.resize(n * ndim);
-    subregions.Length.resize(n * ndim);
-    pagani_b200::check(
-      pgn_regions_export(ctx_, subregions.LeftCoord.data(), subregions.Length.data(), n, &n),
-      "pgn_regions_export");
-    subregions.size = n;
-  }
-
   pgn_ctx* context() { return ctx_; }
 
 private:
   template <typename IntegT>
   numint::integration_result
   run(const IntegT& integrand, T epsrel, T epsabs, quad::Volume<T, ndim> const& vol,
-      bool relerr_classification, bool caller_regions)
+      bool relerr_classification, bool caller_regions, const std::string& id = "default")
   {
     pagani_b200::check(pgn_set_volume(ctx_, vol.lows, vol.highs), "pgn_set_volume");
     pagani_b200::Evaluator<IntegT, static_cast<int>(ndim)> evaluator(integrand);
@@ -227,7 +96,44 @@ private:
     out.lastPhase = r.lastPhase;
     out.chi_sq = r.chi_sq;
     out.iters = r.iters;
+    if constexpr (debug > 0)
+      write_recorders(epsrel, id);
     return out;
+  }
+
+  // debug > 0: the reference's two recorder files (Workspace.cuh:171-242; Recorder, common/cuda/cudaDebugUtil.h:18-37),
+  // same names, header lines and columns, written from the engine's per-iteration trace once the call has ended
+  // (truncated per call, appended with collect_mult_runs):
+  //   cuda_pagani_iters.csv           it, estimate, errorest, festimate, ferrorest, nregions, nfregions
+  //   cuda_pagani_time_breakdown.csv  id, ndim, epsrel, it, name, time   (device milliseconds per stage)
+  void
+  write_recorders(T epsrel, const std::string& id)
+  {
+    const auto mode = collect_mult_runs ? std::ios_base::app : std::ios_base::out;
+    std::ofstream iters("cuda_pagani_iters.csv", mode), times("cuda_pagani_time_breakdown.csv", mode);
+    if (!collect_mult_runs) {
+      iters << "it, estimate, errorest, festimate, ferrorest, nregions, nfregions" << std::endl;
+      times << "id, ndim, epsrel, it, name, time" << std::endl;
+    }
+    double cum_est = 0., cum_err = 0.;
+    size_t finished_regions = 0;
+    const int n = pgn_trace_count(ctx_);
+    for (int i = 0; i < n; ++i) {
+      pgn_iter_stats st;
+      if (pgn_trace_get(ctx_, i, &st) != PGN_OK)
+        break;
+      // the reference prints before this iteration's finished regions are added (Workspace.cuh:230-241)
+      iters << st.iteration << "," << cum_est + st.iter_estimate << "," << cum_err + st.iter_errorest << "," << cum_est
+            << "," << cum_err << "," << st.nregions_global << "," << finished_regions << std::endl;
+      const char* names[4] = {"apply_cubature_rules", "two_level_errorest", "heuristic_classify", "filter_and_split"};
+      const double ms[4] = {st.eval_ms, st.classify_ms, st.heuristic_ms, st.split_ms};
+      for (int k = 0; k < 4; ++k)
+        times << id << "," << ndim << "," << epsrel << "," << st.iteration << "," << names[k] << "," << ms[k]
+              << std::endl;
+      cum_est = st.cum_estimate;
+      cum_err = st.cum_errorest;
+      finished_regions += st.nregions_global - st.nactive;
+    }
   }
 
   pgn_ctx* ctx_ = nullptr;

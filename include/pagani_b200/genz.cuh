@@ -212,34 +212,8 @@ struct Gaussian {
 #endif
     return PGN_GENZ_EXP(-1.0 * s);
   }
-#if defined(__CUDACC__) && PGN_GENZ_FAST_POW && !defined(PGN_GENZ_LIBRARY_MATH) && !defined(PGN_GENZ_NO_BATCH)
-  // call-free form (evaluate.cuh: has_batch_fast): the library's pow(x, 2.) operation sequence without its
-  // special-case branch (the only CALL of this functor); false when it would have been taken.  exp() is inline code
-  // in either form.
-  template <int M>
-  __device__ bool
-  batch_fast(const double (&x)[M][N], double (&f)[M]) const
-  {
-    const double beta = .5;
-    bool ok = true;
-#pragma unroll
-    for (int m = 0; m < M; ++m) {
-      double sq[N];
-#pragma unroll
-      for (int k = 0; k < N; ++k) {
-        bool okk;
-        sq[k] = ::pagani_b200::fastmath::pow2_fast(x[m][k] - beta, &okk);
-        ok = ok && okk;
-      }
-      double s = pow(25., 2.) * sq[0];
-#pragma unroll
-      for (int k = 1; k < N; ++k)
-        s = s + pow(25., 2.) * sq[k];
-      f[m] = PGN_GENZ_EXP(-1.0 * s);
-    }
-    return ok;
-  }
-#endif
+  // (no batch_fast form: interleaving the 2 x N pow kernels of two points without a branch between them measured
+  // 10-14 % SLOWER than operator() per point -- register pressure -- profiles/r02_evalbench_d.jsonl)
 };
 
 // F_5: exp(-10 sum_k |x_k - .5|)
@@ -279,6 +253,29 @@ struct CZero {
         t[m] = fma_rn(-10., fabs(x[m][k] - beta), t[m]);
     }
     ::pagani_b200::fastmath::exp_pinned_n<M>(t, f);
+  }
+#endif
+#if defined(__CUDACC__) && !defined(PGN_GENZ_LIBRARY_MATH) && !defined(PGN_GENZ_NO_BATCH)
+  // branch-free form (evaluate.cuh: has_batch_fast): false when exp() would have left its direct range (never on the
+  // unit cube: the exponent is >= -5 N); +9 % at 10-D over the batch form with its cold branch
+  template <int M>
+  __device__ bool
+  batch_fast(const double (&x)[M][N], double (&f)[M]) const
+  {
+    const double beta = .5;
+    bool ok = true;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      double t = mul_rn(-10., fabs(x[m][1] - beta));
+      t = fma_rn(-10., fabs(x[m][0] - beta), t);
+#pragma unroll
+      for (int k = 2; k < N; ++k)
+        t = fma_rn(-10., fabs(x[m][k] - beta), t);
+      bool oke;
+      f[m] = ::pagani_b200::fastmath::exp_fast(t, &oke);
+      ok = ok && oke;
+    }
+    return ok;
   }
 #endif
 };

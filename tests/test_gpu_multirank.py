@@ -130,3 +130,35 @@ def test_nccl_in_kernel_search_follows_single_rank(pg, tmp_path):
         assert (rk["status"], rk["nregions"], rk["iters"]) == (r1.status, r1.nregions, r1.iters)
         assert abs(rk["estimate"] - r1.estimate) <= 1e-12 * max(abs(r1.estimate), r1.errorest)
         assert rk["estimate"] == ranks[0]["estimate"] and rk["errorest"] == ranks[0]["errorest"]
+
+
+def _golden(family, ndim, eps):
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "trajectories", f"f{family}_{ndim}_{eps:g}.json")
+    return json.load(open(path))
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("family,ndim,epsrel", [(1, 8, 1e-4), (4, 8, 1e-9), (5, 10, 1e-3)])
+def test_nccl_ranks_follow_the_reference_golden(tmp_path, world, family, ndim, epsrel):
+    """One process per GPU over NCCL + the in-kernel NVLink exchanges (fused statistics, threshold search): every rank
+    must walk through the trajectory the UNMODIFIED single-GPU reference recorded (tests/golden/trajectories) --
+    global region counts, survivors and heuristic-filter decisions per iteration, status / nregions / iters, estimate
+    to 1e-12.  (4, 8, 1e-9) is BASELINE config 5: F_4_8D, epsrel 1e-9, partitioned region list."""
+    import torch
+
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    doc = _golden(family, ndim, epsrel)
+    its, s = doc["iterations"], doc["summary"]
+    ranks = _run(tmp_path, world, "nccl", family, ndim, epsrel)
+    for rk in ranks:
+        assert rk["n_global"] == [r["n"] for r in its]
+        assert rk["heuristic_ran"] == [r["heuristic_ran"] for r in its]
+        for i, r in enumerate(its):
+            if r["outcome"] == "split":
+                assert rk["nactive"][i] == r["nactive"], i
+        assert (rk["status"], rk["nregions"], rk["iters"]) == (s["status"], s["nregions"], s["iters"])
+        assert abs(rk["estimate"] - s["estimate"]) <= 1e-12 * max(abs(s["estimate"]), s["errorest"])
+        assert rk["estimate"] == ranks[0]["estimate"] and rk["errorest"] == ranks[0]["errorest"]
+    for i in range(len(its)):
+        assert sum(rk["n_local"][i] for rk in ranks) == its[i]["n"]

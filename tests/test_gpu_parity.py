@@ -161,3 +161,28 @@ def test_non_unit_volume_against_cpu_oracle(pg, lows, highs):
     area = np.prod(highs - lows)
     want = (highs[0] ** 2 - lows[0] ** 2) * (highs[1] ** 2 - lows[1] ** 2) / 4
     assert est.sum() == pytest.approx(want, rel=1e-12, abs=1e-12 * area)
+
+
+@pytest.mark.parametrize("family,ndim,parts,lows,highs", [
+    (1, 8, 2, 0.0, 1e9),    # sum k*x_k up to 3.6e10: cos() needs its Payne-Hanek path for most points
+    (1, 8, 2, 0.0, 3e8),    # ... for SOME points of a region
+    (5, 5, 2, 0.0, 200.0),  # exponent down to -9975: exp() leaves its direct range (underflow to 0)
+    (5, 10, 2, -30.0, 40.0),
+    (4, 5, 1, 0.0, 1.0),    # one region centred on the peak: x - .5 == 0 takes pow()'s special-case path
+    (4, 8, 1, 0.0, 1.0),
+])
+def test_exact_fallback_matches_operator_path(pg, family, ndim, parts, lows, highs):
+    """Functors with the call-free batch_fast form (evaluate.cuh): a region in which some point needs the functor's
+    slow path is re-evaluated through operator().  The byte-permute kernel (batch_fast + fallback) and the shift/mask
+    kernel (operator() only) must agree bit for bit on such regions."""
+    out = []
+    for variant in (1, 2):
+        with pg.Workspace(ndim) as ws:
+            ws.set_eval_variant(variant)
+            ws.set_volume(pg.Volume(ndim, np.full(ndim, lows), np.full(ndim, highs)))
+            ws.uniform_split(parts)
+            ws.apply_cubature_integration_rules(pg.Genz(family, ndim))
+            out.append(ws.fetch_estimates()[:3])
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    assert np.all(np.isfinite(out[0][0]))
