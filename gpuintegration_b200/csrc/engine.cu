@@ -1,6 +1,8 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -235,6 +237,8 @@ Engine::~Engine()
     cudaFreeHost(host_local_);
   if (host_global_)
     cudaFreeHost(host_global_);
+  if (host_pub_)
+    cudaFreeHost(host_pub_);
   if (host_search_)
     cudaFreeHost(host_search_);
   for (cudaEvent_t e : ev_pool_)
@@ -295,6 +299,22 @@ Engine::init()
   PGN_TRY(digest_dev_.reserve(sizeof(unsigned long long) * 8));
   PGN_CUDA(cudaMallocHost(&host_local_, sizeof(double) * kHostStats));
   PGN_CUDA(cudaMallocHost(&host_global_, sizeof(double) * kHostStats));
+  if (!std::getenv("PGN_NO_ZERO_COPY_STATS")) {
+    void* pub = nullptr;
+    if (cudaHostAlloc(&pub, sizeof(double) * (2 * kHostStats + 1), cudaHostAllocMapped) == cudaSuccess) {
+      std::memset(pub, 0, sizeof(double) * (2 * kHostStats + 1));
+      void* dev = nullptr;
+      if (cudaHostGetDevicePointer(&dev, pub, 0) == cudaSuccess) {
+        host_pub_ = static_cast<double*>(pub);
+        host_pub_dev_ = static_cast<double*>(dev);
+      } else {
+        cudaGetLastError();
+        cudaFreeHost(pub);
+      }
+    } else {
+      cudaGetLastError();
+    }
+  }
   rank_counts_.assign(1, 0);
   // bucket tables: count, start(+1), cursor, bucket_sum, suffix_sum(+1), suffix_count(+1), outside, acc_lo, acc_hi
   PGN_TRY(search_tab_.reserve(8 * (8 * static_cast<size_t>(kMaxBuckets) + 8)));
@@ -519,10 +539,53 @@ Engine::launch_evaluate_on(pgn_eval_fn fn, void* user, const double* left, const
   return rc;
 }
 
+// Wait until the statistics kernel number pub_seq_ has raised its flag in host-mapped memory.  The stream is queried
+// now and then so that a failed launch or a sticky error ends the wait.
+int
+Engine::wait_published()
+{
+  volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(host_pub_ + 2 * kHostStats);
+  unsigned long spins = 0;
+  while (*flag != pub_seq_) {
+    if ((++spins & 0x3fffu) == 0) {
+      const cudaError_t q = cudaStreamQuery(stream_);
+      if (q == cudaSuccess) {
+        if (*flag == pub_seq_)
+          break;
+        set_last_error("statistics kernel finished without publishing its result");
+        return PGN_ERR_CUDA;
+      }
+      if (q != cudaErrorNotReady) {
+        set_last_error(std::string("statistics kernel failed: ") + cudaGetErrorString(q));
+        return PGN_ERR_CUDA;
+      }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return PGN_OK;
+}
+
 int
 Engine::sync_stats(bool need_minmax)
 {
   const bool multi = comm_ && comm_->nranks > 1;
+  if (stats_published_ && (!multi || stats_fused_)) {
+    // zero-copy path: both vectors are already (or will shortly be) in pinned host memory
+    PGN_TRY(wait_published());
+    std::memcpy(host_local_, host_pub_, sizeof(double) * kStatsLen);
+    std::memcpy(host_global_, host_pub_ + kStatsLen, sizeof(double) * kStatsLen);
+    stats_published_ = false;
+    if (multi && std::isnan(host_global_[kNumActive])) {
+      set_last_error("fused statistics all-reduce: a peer did not answer within the spin limit");
+      return PGN_ERR_NCCL;
+    }
+    const int w = comm_ ? comm_->nranks : 1;
+    rank_counts_.resize(w);
+    for (int r = 0; r < w; ++r)
+      rank_counts_[r] = static_cast<size_t>(host_global_[kRankSlot + r]);
+    return PGN_OK;
+  }
+  stats_published_ = false;
   if (multi && stats_fused_) {
     // the statistics kernel all-reduced its vector itself (sums and [-min, max]) over NVLink
     PGN_CUDA(cudaMemcpyAsync(host_global_, stats_glob_.ptr, sizeof(double) * kStatsLen,
@@ -606,6 +669,9 @@ Engine::make_scratch(bool allow_fused)
   ts.rank = comm_ ? comm_->rank : 0;
   ts.nranks = comm_ ? comm_->nranks : 1;
   ts.stats_glob = stats_glob_.as<double>();
+  ts.host_out = host_pub_dev_;
+  ts.host_seq = host_pub_dev_ ? ++pub_seq_ : 0;
+  stats_published_ = host_pub_dev_ != nullptr;
   stats_fused_ = false;
   if (allow_fused && comm_ && comm_->nranks > 1 && peer_ready_) {
     // a peer may still be inside a long evaluation kernel: allow about a minute of skew
@@ -621,7 +687,7 @@ Engine::run_classify(double epsrel, int relerr)
 {
   TileScratch ts = make_scratch();
   if (n_ == 0) {
-    if (stats_fused_)
+    if (stats_fused_ || stats_published_)
       ++launches_, k_publish_empty_stats<<<1, kBlock, 0, stream_>>>(ts);
     else
       PGN_TRY(write_empty_stats(stats_dev_.as<double>(), stream_));
@@ -647,7 +713,7 @@ Engine::run_threshold(int mode, double threshold)
 {
   TileScratch ts = make_scratch();
   if (n_ == 0) {
-    if (stats_fused_) {
+    if (stats_fused_ || stats_published_) {
       ++launches_, k_publish_empty_stats<<<1, kBlock, 0, stream_>>>(ts);
       return cudaGetLastError() == cudaSuccess ? PGN_OK : PGN_ERR_CUDA;
     }
@@ -672,7 +738,7 @@ Engine::run_recount()
 {
   TileScratch ts = make_scratch();
   if (n_ == 0) {
-    if (stats_fused_) {
+    if (stats_fused_ || stats_published_) {
       ++launches_, k_publish_empty_stats<<<1, kBlock, 0, stream_>>>(ts);
       return cudaGetLastError() == cudaSuccess ? PGN_OK : PGN_ERR_CUDA;
     }
@@ -1027,6 +1093,7 @@ Engine::dev_evaluate(pgn_eval_fn fn, void* user, const double* d_left, const dou
       ++launches_, k_fill_f64<<<blocks_for(n, 256), 256, 0, stream_>>>(d_active_f64, n, 1.0);
     // the two sums it returns (:336-341): one pass of the classify kernel without refinement
     TileScratch ts = make_scratch(false);
+    stats_published_ = false;  // read back below with an explicit copy
     ++launches_, k_classify<false><<<super_tiles_for(tiles_for(n)), kBlock, 0, stream_>>>(
       d_est, d_err, nullptr, nullptr, active_.as<uint8_t>(), n, 0.0, 0, static_cast<unsigned int>(tiles_for(n)), ts);
     PGN_CUDA(cudaGetLastError());
@@ -1054,6 +1121,7 @@ Engine::dev_count_active(const double* d_active_f64, size_t n, size_t* count)
   PGN_TRY(ensure_iteration_buffers(n));
   ++launches_, k_flags_from_f64<<<blocks_for(n, 256), 256, 0, stream_>>>(d_active_f64, active_.as<uint8_t>(), n);
   TileScratch ts = make_scratch(false);
+  stats_published_ = false;  // read back below with an explicit copy
   // the flag array doubles as the (unused) value arrays of the counting kernel
   ++launches_, k_recount<<<tiles_for(n), kBlock, 0, stream_>>>(d_active_f64, d_active_f64, active_.as<uint8_t>(), n,
                                                                 ts);
@@ -1507,6 +1575,7 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
                                                    stats_dev_.as<double>() + kSumActErr);
       PGN_CUDA(cudaGetLastError());
       stats_fused_ = false;  // k_query is not a statistics kernel: its two numbers go through the communicator
+      stats_published_ = false;
       if (first_probe) {
         // the number of values the buckets cannot represent travels in an otherwise unused slot
         ++launches_, k_outside_to_double<<<1, 1, 0, stream_>>>(tables.outside,
@@ -1671,20 +1740,34 @@ Engine::integrate(pgn_eval_fn fn, void* user, const pgn_integrate_args& args, pg
       ev_recorded[idx] = 1;
   };
 
+  // PGN_HOST_TIMING=1: where the host spends an integrate() call (stderr, one line per call)
+  static const bool host_timing = std::getenv("PGN_HOST_TIMING") != nullptr;
+  using Clock = std::chrono::steady_clock;
+  double t_launch = 0, t_sync = 0, t_heur = 0, t_split = 0;
+  const Clock::time_point t_call = Clock::now();
+  auto since = [](Clock::time_point t0) { return std::chrono::duration<double, std::micro>(Clock::now() - t0).count(); };
+  int n_iters_run = 0;
+
   for (int it = 0; it < max_iters && n_global > 0 && !done; ++it) {
+    ++n_iters_run;
     pgn_iter_stats st;
     std::memset(&st, 0, sizeof st);
     st.iteration = it;
     st.nregions = n_;
     st.nregions_global = n_global;
 
-    mark(it, kEvStart);
+    Clock::time_point t0 = Clock::now();
+    if (it == 0)
+      mark(it, kEvStart);  // later iterations start where the previous one's split ended
     PGN_TRY(launch_evaluate(fn, user));
     evaluated_ = true;
     mark(it, kEvEvaluated);
     PGN_TRY(run_classify(epsrel, relerr));
     mark(it, kEvClassified);
+    t_launch += since(t0);
+    t0 = Clock::now();
     PGN_TRY(sync_stats(false));
+    t_sync += since(t0);
     neval += static_cast<uint64_t>(n_global) * rule_.feval;
 
     const double iter_est = host_global_[kSumEst];
@@ -1739,9 +1822,12 @@ Engine::integrate(pgn_eval_fn fn, void* user, const pgn_integrate_args& args, pg
     }
 
     HeuristicOutcome hs;
-    mark(it, kEvHeuristicBegin);
+    t0 = Clock::now();
+    if (st.budget_overflow)
+      mark(it, kEvHeuristicBegin);  // otherwise nothing ran since kEvClassified
     PGN_TRY(heuristic_classify(n_global, iter_est, iter_err, fin_err, cum_err, &hs));
     mark(it, kEvHeuristicEnd);
+    t_heur += since(t0);
     st.heuristic_ran = hs.ran;
     st.heuristic_probes = hs.probes;
     st.threshold = hs.threshold;
@@ -1783,7 +1869,9 @@ Engine::integrate(pgn_eval_fn fn, void* user, const pgn_integrate_args& args, pg
     } else {
       rank_counts_ = counts;
       bool rebalanced = false;
+      t0 = Clock::now();
       PGN_TRY(compact_and_split(m_local, m_global, &rebalanced));
+      t_split += since(t0);
       st.rebalanced = rebalanced;
       n_global = 2 * m_global;
     }
@@ -1797,10 +1885,20 @@ Engine::integrate(pgn_eval_fn fn, void* user, const pgn_integrate_args& args, pg
   if (!done)
     nregions += n_global;
   PGN_CUDA(cudaStreamSynchronize(stream_));
+  if (host_timing)
+    std::fprintf(stderr, "[pgn host] %d iterations, %.0f us in the call: launching evaluate+classify %.0f, waiting for the "
+                         "statistics %.0f, heuristic %.0f, compact/split launch %.0f\n",
+                 n_iters_run, since(t_call), t_launch, t_sync, t_heur, t_split);
   if (tracing) {
     auto elapsed = [&](int it, int a, int b) -> double {
-      const size_t ia = static_cast<size_t>(it) * kEvPerIter + a, ib = static_cast<size_t>(it) * kEvPerIter + b;
-      if (ib >= ev_recorded.size() || !ev_recorded[ia] || !ev_recorded[ib])
+      size_t ia = static_cast<size_t>(it) * kEvPerIter + a;
+      const size_t ib = static_cast<size_t>(it) * kEvPerIter + b;
+      // events that were not recorded because they coincide with an earlier one
+      if (a == kEvStart && it > 0)
+        ia = static_cast<size_t>(it - 1) * kEvPerIter + kEvSplit;
+      if (a == kEvHeuristicBegin && (ia >= ev_recorded.size() || !ev_recorded[ia]))
+        ia = static_cast<size_t>(it) * kEvPerIter + kEvClassified;
+      if (ia >= ev_recorded.size() || ib >= ev_recorded.size() || !ev_recorded[ia] || !ev_recorded[ib])
         return 0.0;
       float ms = 0;
       return cudaEventElapsedTime(&ms, ev_pool_[ia], ev_pool_[ib]) == cudaSuccess ? ms : 0.0;

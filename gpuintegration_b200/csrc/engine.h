@@ -175,6 +175,12 @@ private:
   DeviceBuf partials_, tile_count_, tile_offset_, done_, stats_dev_, stats_glob_, digest_dev_;
   double* host_local_ = nullptr;   // pinned [kHostStats]
   double* host_global_ = nullptr;  // pinned [kHostStats]
+  // zero-copy statistics: host-mapped [2 * kHostStats doubles + 1 word], written by the statistics kernels
+  double* host_pub_ = nullptr;
+  double* host_pub_dev_ = nullptr;       // device address of host_pub_
+  unsigned long long pub_seq_ = 0;       // number of the last publishing kernel enqueued
+  bool stats_published_ = false;         // the last statistics kernel publishes (sync_stats polls instead of copying)
+  int wait_published();
   std::vector<size_t> rank_counts_;  // active regions per rank after the last flag-changing stage
   // rebalance staging
   DeviceBuf pack_send_, pack_recv_;

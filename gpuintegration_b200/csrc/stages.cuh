@@ -55,6 +55,11 @@ struct TileScratch {
   double* stats_glob;
   unsigned long long seq;
   PeerBox box;
+  // zero-copy publication: when set, the kernel's last block also stores `stats` (and `stats_glob`) into this
+  // host-mapped buffer [2 * kStatsLen doubles + one 64-bit word] and then raises the word to host_seq, so the host
+  // driver polls pinned memory instead of enqueueing a copy and synchronising the stream after every iteration
+  double* host_out;
+  unsigned long long host_seq;
 };
 // layout of `stats`: [0,8) the Stat slots; [8] = -min(err), [9] = max(err) (so one MAX all-reduce
 // serves both); [16 + r] = active regions of rank r (zero except the own rank: a SUM all-reduce of
@@ -144,6 +149,23 @@ block_reduce(Acc a, Acc* s_warp /*[kBlock/32]*/)
   return a;
 }
 
+// Last step of a statistics kernel (one block): copy the final vectors into host-mapped memory, fence, raise the flag.
+__device__ __forceinline__ void
+publish_to_host(const TileScratch& ts)
+{
+  if (ts.host_out == nullptr)
+    return;
+  __syncthreads();  // ts.stats / ts.stats_glob were written by threads of this block
+  if (threadIdx.x < kStatsDoubles) {
+    ts.host_out[threadIdx.x] = ts.stats[threadIdx.x];
+    ts.host_out[kStatsDoubles + threadIdx.x] = ts.box.nranks > 1 ? ts.stats_glob[threadIdx.x] : ts.stats[threadIdx.x];
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    *reinterpret_cast<volatile unsigned long long*>(ts.host_out + 2 * kStatsDoubles) = ts.host_seq;
+}
+
 // Executed by every block after it stored its partial: the last block to arrive folds the
 // partials in a fixed order, writes the final statistics and the exclusive prefix of the tile
 // counts, and re-arms the counter.
@@ -217,6 +239,7 @@ finalize(const TileScratch& ts, unsigned int tiles, bool with_offsets, Acc* s_wa
     __syncthreads();
     peer_allreduce_stats(ts.box, ts.seq, ts.stats, ts.stats_glob, kNegMinSlot, kMaxSlot + 1, &s_peer_ok);
   }
+  publish_to_host(ts);
 }
 
 }  // namespace dev
@@ -270,41 +293,22 @@ k_classify(const double* __restrict__ est, const double* __restrict__ err_raw,
   dev::Acc a;
   dev::acc_zero(a);
   // The 16 rounds of a super-tile (256 regions each) run as a software pipeline of depth kDepth: the five loads of
-  // round r + kDepth are issued before the arithmetic of round r, so a thread always has 5 * kDepth loads in flight
-  // while it computes (one correctly rounded FP64 division and seven accumulations per region: about as many FP64
-  // pipe cycles as the 29 bytes cost in HBM time -- a load-everything-then-compute loop pays both in turn).
+  // round r + kDepth are issued before the arithmetic of round r.
+  //
+  // Addressing: ncu showed this kernel bound by ISSUE SLOTS, not by HBM -- 140 instructions per region, 65 of them
+  // 64-bit index arithmetic (clamped region index, sibling = i +- n/2, parent = i mod n/2, five array addresses, per
+  // round).  A super-tile that exists completely and lies on one side of the list's midpoint (all but at most two)
+  // therefore takes the FAST path: five per-thread base pointers computed once, every access of the 16 rounds at a
+  // compile-time byte offset from them.
   constexpr int kSteps = kSuper * kRounds;
   constexpr int kDepth = PGN_CLASSIFY_DEPTH;
   const size_t sbase = static_cast<size_t>(sup) * kSuper * kTile;
   struct Stage {
     double est, err, sib_est, sib_err, par;
   };
-  Stage st[kDepth];
-  auto load = [&](int step, Stage& s) {
-    size_t i = sbase + static_cast<size_t>(step) * kBlock + threadIdx.x;
-    i = i < n ? i : n - 1;  // clamped: the loads are unconditional
-    s.est = est[i];
-    s.err = err_raw[i];
-    if constexpr (REFINE) {
-      const bool right = (i + i) >= n;
-      const size_t sib = right ? i - half : i + half;
-      const size_t par = right ? i - half : i;
-      s.sib_est = est[sib];
-      s.sib_err = err_raw[sib];
-      s.par = parent_est[par];
-    }
-  };
-#pragma unroll
-  for (int d = 0; d < kDepth; ++d)
-    load(d, st[d]);
-  int my_active = 0;
-#pragma unroll
-  for (int step = 0; step < kSteps; ++step) {
-    const Stage cur = st[step % kDepth];
-    if (step + kDepth < kSteps)
-      load(step + kDepth, st[step % kDepth]);
-    const size_t i = sbase + static_cast<size_t>(step) * kBlock + threadIdx.x;
-    if (i < n) {
+  int my_active = 0, n_active = 0;
+  auto process = [&](const Stage& cur, bool exists, double* err_dst, uint8_t* flag_dst) {
+    if (exists) {
       const double self_est = cur.est;
       double e = cur.err;
       double flag = 1.0;
@@ -317,30 +321,96 @@ k_classify(const double* __restrict__ est, const double* __restrict__ err_raw,
           e = __dmul_rn(e, c);
         }
         e = __dadd_rn(diff, e);
-        err_out[i] = e;
+        *err_dst = e;
         if (relerr_classification) {
-          const double tol = fmax(__dmul_rn(epsrel, fabs(self_est)), 1e-200);
+          // fmax(epsrel * |est|, 1e-200) without the library's NaN plumbing (a NaN product selects 1e-200 either way)
+          const double t = __dmul_rn(epsrel, fabs(self_est));
+          const double tol = t > 1e-200 ? t : 1e-200;
           flag = (e < tol) ? 0.0 : 1.0;
         }
       }
-      active[i] = flag != 0.0 ? 1 : 0;
+      *flag_dst = flag != 0.0 ? 1 : 0;
       my_active += flag != 0.0 ? 1 : 0;
       a.v[kSumEst] += self_est;
       a.v[kSumErr] += e;
       a.v[kSumActEst] += flag * self_est;  // thrust::inner_product(flags, estimates)
       a.v[kSumActErr] += flag * e;
-      a.v[kNumActive] += flag;
-      a.mn = fmin(a.mn, e);
-      a.mx = fmax(a.mx, e);
+      // (the count of active regions is kept as an integer, n_active, and converted once: sums of 1.0 are exact)
+      // min / max as compare-and-select: a NaN error leaves both untouched, like fmin / fmax
+      a.mn = e < a.mn ? e : a.mn;
+      a.mx = e > a.mx ? e : a.mx;
     }
+  };
+  auto end_of_round = [&](int step) {
     if ((step % kRounds) == kRounds - 1) {
       // active regions of the tile just finished: warp sums into a shared counter (integers: order does not matter)
       const int warp_active = __reduce_add_sync(0xffffffffu, my_active);
       if ((threadIdx.x & 31) == 0 && warp_active)
         atomicAdd(&s_tile_active[step / kRounds], static_cast<unsigned int>(warp_active));
+      n_active += my_active;
       my_active = 0;
     }
+  };
+  const size_t send = sbase + static_cast<size_t>(kSuper) * kTile;  // one past the super-tile
+  const bool whole = send <= n;
+  const bool one_side = !REFINE || send <= half || sbase >= half;
+  if (whole && one_side) {  // block-uniform
+    const double* p_est = est + sbase + threadIdx.x;
+    const double* p_err = err_raw + sbase + threadIdx.x;
+    const double* p_sib_est = p_est;
+    const double* p_sib_err = p_err;
+    const double* p_par = nullptr;
+    double* p_out = REFINE ? err_out + sbase + threadIdx.x : nullptr;
+    uint8_t* p_flag = active + sbase + threadIdx.x;
+    if constexpr (REFINE) {
+      const bool right = sbase >= half;
+      p_sib_est = right ? p_est - half : p_est + half;
+      p_sib_err = right ? p_err - half : p_err + half;
+      p_par = parent_est + (right ? sbase - half : sbase) + threadIdx.x;
+    }
+    Stage st[kDepth];
+    auto load = [&](int step, Stage& s) {
+      s.est = p_est[step * kBlock];
+      s.err = p_err[step * kBlock];
+      if constexpr (REFINE) {
+        s.sib_est = p_sib_est[step * kBlock];
+        s.sib_err = p_sib_err[step * kBlock];
+        s.par = p_par[step * kBlock];
+      }
+    };
+#pragma unroll
+    for (int d = 0; d < kDepth; ++d)
+      load(d, st[d]);
+#pragma unroll
+    for (int step = 0; step < kSteps; ++step) {
+      const Stage cur = st[step % kDepth];
+      if (step + kDepth < kSteps)
+        load(step + kDepth, st[step % kDepth]);
+      process(cur, true, p_out + step * kBlock, p_flag + step * kBlock);
+      end_of_round(step);
+    }
+  } else {
+    // generic path (the last super-tile and the one that straddles the midpoint): clamped 64-bit indices
+#pragma unroll 1
+    for (int step = 0; step < kSteps; ++step) {
+      const size_t i0 = sbase + static_cast<size_t>(step) * kBlock + threadIdx.x;
+      const size_t i = i0 < n ? i0 : n - 1;
+      Stage cur;
+      cur.est = est[i];
+      cur.err = err_raw[i];
+      if constexpr (REFINE) {
+        const bool right = (i + i) >= n;
+        const size_t sib = right ? i - half : i + half;
+        const size_t par = right ? i - half : i;
+        cur.sib_est = est[sib];
+        cur.sib_err = err_raw[sib];
+        cur.par = parent_est[par];
+      }
+      process(cur, i0 < n, REFINE ? err_out + i : nullptr, active + i);
+      end_of_round(step);
+    }
   }
+  a.v[kNumActive] = static_cast<double>(n_active);
   __syncthreads();
   if (threadIdx.x < kSuper && sup * kSuper + threadIdx.x < tiles)
     ts.tile_count[sup * kSuper + threadIdx.x] = s_tile_active[threadIdx.x];
@@ -455,8 +525,12 @@ k_publish_empty_stats(TileScratch ts)
   __syncthreads();
   if (ts.box.nranks > 1)
     peer_allreduce_stats(ts.box, ts.seq, ts.stats, ts.stats_glob, kNegMinSlot, kMaxSlot + 1, &s_peer_ok);
+  dev::publish_to_host(ts);
 }
 
+#ifndef PGN_COMPACT_AXES
+#define PGN_COMPACT_AXES 8
+#endif
 struct CompactArgs {
   const double* left;       // [ndim][n]
   const double* length;     // [ndim][n]
@@ -517,18 +591,21 @@ k_compact(const CompactArgs A)
       A.parent_err[j] = A.err[i];
       if (!FUSED)
         A.out_axis[j] = ax;
-      // four axes at a time: eight independent loads in flight per thread before the first store
-      // (the output pointers may alias the inputs as far as the compiler knows)
-      for (int d0 = 0; d0 < A.ndim; d0 += 4) {
-        double lo[4], ln[4];
+      // kAxes axes at a time: 2 * kAxes independent loads in flight per thread before the first store (the output
+      // pointers may alias the inputs as far as the compiler knows).  With half of the lanes predicated off -- the
+      // usual survival rate of the large iterations -- a tile has half the loads in flight; eight axes at a time
+      // keep the kernel bandwidth-bound there too.
+      constexpr int kAxes = PGN_COMPACT_AXES;
+      for (int d0 = 0; d0 < A.ndim; d0 += kAxes) {
+        double lo[kAxes], ln[kAxes];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < kAxes; ++k) {
           const int d = d0 + k < A.ndim ? d0 + k : A.ndim - 1;
           lo[k] = __ldcs(&A.left[static_cast<size_t>(d) * A.n + i]);
           ln[k] = __ldcs(&A.length[static_cast<size_t>(d) * A.n + i]);
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < kAxes; ++k) {
           const int d = d0 + k;
           if (d < A.ndim) {
             double* ol = A.out_left + static_cast<size_t>(d) * out_stride;

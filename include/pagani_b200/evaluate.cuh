@@ -36,6 +36,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <new>
 #include <type_traits>
 #include <utility>
@@ -243,40 +244,64 @@ warp_argmax_first(double& v, int& idx)
 
 // ---- per-region prologue: bounds, volume, default axis, coordinate table -------------------------
 // (INIT_REGION_POOL, Phases.cuh:323-349, and the affine map of computePermutation, Sample.cuh:124-131)
+// bounds of region `reg` on axis `lane` (lanes < NDIM): the only global loads of a region
 template <int NDIM>
 __device__ __forceinline__ void
-region_prologue(const EvalParams& P, size_t reg, int lane, const double* s_tp, const double* s_tm,
+load_bounds(const EvalParams& P, size_t reg, int lane, double& lo, double& len)
+{
+  if (lane < NDIM) {
+    lo = P.left[static_cast<size_t>(lane) * P.n + reg];
+    len = P.length[static_cast<size_t>(lane) * P.n + reg];
+  }
+}
+
+template <int NDIM>
+__device__ __forceinline__ void
+region_prologue(const EvalParams& P, double lo, double len, int lane, const double* s_tp, const double* s_tm,
                 double* s_lo, double* s_up, double* s_ext, double* s_x, double& vol, int& max_dim)
 {
-  constexpr int kArgWidth = NDIM <= 16 ? 16 : 32;
-  const size_t n = P.n;
   if (lane < NDIM) {
-    const double lo = P.left[static_cast<size_t>(lane) * n + reg];
-    const double up = __dadd_rn(lo, P.length[static_cast<size_t>(lane) * n + reg]);
+    const double up = __dadd_rn(lo, len);
     s_lo[lane] = lo;
     s_up[lane] = up;
     s_ext[lane] = __dsub_rn(up, lo);
   }
   __syncwarp();
-  vol = s_ext[0];
-#pragma unroll
-  for (int d = 1; d < NDIM; ++d)
-    vol = __dmul_rn(vol, s_ext[d]);
+  // volume and longest axis from the NDIM extents, which every lane reads anyway (broadcast loads): the product in
+  // axis order (Phases.cuh:331-333) and the FIRST axis with the largest positive extent (:344-347), in registers --
+  // no shuffle rounds
   {
-    double e = 0.0;
-    int idx = lane;
-    if (lane < NDIM) {
-      const double v = s_ext[lane];
-      e = v > 0.0 ? v : 0.0;
+    double ext[NDIM];
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d)
+      ext[d] = s_ext[d];
+    vol = ext[0];
+    double best = 0.0;
+    max_dim = 0;
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d) {
+      if (d > 0)
+        vol = __dmul_rn(vol, ext[d]);
+      if (ext[d] > best) {
+        best = ext[d];
+        max_dim = d;
+      }
     }
-    warp_argmax_first<kArgWidth>(e, idx);
-    max_dim = e > 0.0 ? idx : 0;
   }
-  for (int e = lane; e < NDIM * PGN_NCODES; e += 32) {
-    const int d = e / PGN_NCODES;
-    const int c = e - d * PGN_NCODES;
-    const double inner = __fma_rn(s_tp[c], s_lo[d], __dmul_rn(s_tm[c], s_up[d]));
-    s_x[e] = __fma_rn(P.ranges[d], inner, P.lows[d]);
+  // coordinate table: lane -> (axis = lane / 4, codes lane % 4 + {0, 4, 8}), eight axes per pass; no index division,
+  // one load of the axis' bounds per lane
+#pragma unroll
+  for (int d0 = 0; d0 < NDIM; d0 += 8) {
+    const int d = d0 + (lane >> 2);
+    if (d < NDIM) {
+      const double lo_d = s_lo[d], up_d = s_up[d];
+      const double range = P.ranges[d], low = P.lows[d];
+#pragma unroll
+      for (int c = lane & 3; c < PGN_NCODES; c += 4) {
+        const double inner = __fma_rn(s_tp[c], lo_d, __dmul_rn(s_tm[c], up_d));
+        s_x[d * PGN_NCODES + c] = __fma_rn(range, inner, low);
+      }
+    }
   }
   __syncwarp();
 }
@@ -441,7 +466,11 @@ evaluate_kernel(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const __gr
     __syncwarp();
     double vol;
     int max_dim;
-    region_prologue<NDIM>(P, reg, lane, s_tp, s_tm, s_lo, s_up, s_ext, s_x, vol, max_dim);
+    {
+      double lo = 0.0, len = 0.0;
+      load_bounds<NDIM>(P, reg, lane, lo, len);
+      region_prologue<NDIM>(P, lo, len, lane, s_tp, s_tm, s_lo, s_up, s_ext, s_x, vol, max_dim);
+    }
 
     double sa[PGN_NRULES], sb[PGN_NRULES];
 #pragma unroll
@@ -712,11 +741,22 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
 
   const size_t n = P.n;
   const size_t stride = static_cast<size_t>(gridDim.x) * kWarpsPerBlock;
+  // The bounds of the NEXT region of this warp are loaded while the current one is evaluated: the two global loads
+  // (HBM / L2 latency, several hundred cycles) are the only long-latency operations of a region, and with four to
+  // five warps per scheduler a warp waiting for them at the top of every region costs issue slots.
+  double next_lo = 0.0, next_len = 0.0;
+  {
+    const size_t first = static_cast<size_t>(blockIdx.x) * kWarpsPerBlock + warp;
+    if (first < n)
+      load_bounds<NDIM>(P, first, lane, next_lo, next_len);
+  }
   for (size_t reg = static_cast<size_t>(blockIdx.x) * kWarpsPerBlock + warp; reg < n; reg += stride) {
     __syncwarp();
     double vol;
     int max_dim;
-    region_prologue<NDIM>(P, reg, lane, s_tp, s_tm, s_lo, s_up, s_ext, s_x, vol, max_dim);
+    region_prologue<NDIM>(P, next_lo, next_len, lane, s_tp, s_tm, s_lo, s_up, s_ext, s_x, vol, max_dim);
+    if (reg + stride < n)
+      load_bounds<NDIM>(P, reg + stride, lane, next_lo, next_len);
 
     double sa[PGN_NRULES], sb[PGN_NRULES];
 #pragma unroll
@@ -905,24 +945,33 @@ launch_evaluate(F* functor, const pgn_region_view* v)
   for (int i = 0; i < PGN_NSETS * PGN_NRULES; ++i)
     P.wc[i] = v->rule.weights_host[i];
   if constexpr (NDIM <= 12) {
-    constexpr int kFeval = feval_of(NDIM);
-    static_assert((kFeval + 31) / 32 <= 256, "half_set table too small");
-    auto host_set_of = [](int p) {
-      int st = 0;
-      for (int k = 1; k < PGN_NSETS; ++k)
-        st += p >= set_begin(NDIM, k) ? 1 : 0;
-      return st;
+    // generator set of every 32-point half-chunk / 64-point chunk (0xFF: mixed): a function of NDIM only, built once
+    struct SetTables {
+      uint8_t half_set[256], chunk_set[128];
+      SetTables()
+      {
+        constexpr int kFeval = feval_of(NDIM);
+        static_assert((kFeval + 31) / 32 <= 256, "half_set table too small");
+        auto host_set_of = [](int p) {
+          int st = 0;
+          for (int k = 1; k < PGN_NSETS; ++k)
+            st += p >= set_begin(NDIM, k) ? 1 : 0;
+          return st;
+        };
+        for (int j = 0; j < 256; ++j) {
+          const int first = 32 * j, last = first + 31 < kFeval - 1 ? first + 31 : kFeval - 1;
+          half_set[j] = (first < kFeval && host_set_of(first) == host_set_of(last))
+                          ? static_cast<uint8_t>(host_set_of(first))
+                          : static_cast<uint8_t>(0xFF);
+        }
+        for (int k = 0; k < 128; ++k)
+          chunk_set[k] = (half_set[2 * k] != 0xFF && half_set[2 * k] == half_set[2 * k + 1]) ? half_set[2 * k]
+                                                                                             : static_cast<uint8_t>(0xFF);
+      }
     };
-    for (int j = 0; j < 256; ++j) {
-      const int first = 32 * j, last = first + 31 < kFeval - 1 ? first + 31 : kFeval - 1;
-      P.half_set[j] = (first < kFeval && host_set_of(first) == host_set_of(last))
-                        ? static_cast<uint8_t>(host_set_of(first))
-                        : static_cast<uint8_t>(0xFF);
-    }
-    for (int k = 0; k < 128; ++k)
-      P.chunk_set[k] = (P.half_set[2 * k] != 0xFF && P.half_set[2 * k] == P.half_set[2 * k + 1])
-                         ? P.half_set[2 * k]
-                         : static_cast<uint8_t>(0xFF);
+    static const SetTables tables;
+    std::memcpy(P.half_set, tables.half_set, sizeof P.half_set);
+    std::memcpy(P.chunk_set, tables.chunk_set, sizeof P.chunk_set);
   }
   P.jacobian = v->jacobian;
   P.ratio = v->rule.ratio;

@@ -423,7 +423,7 @@ struct EvalTuning;
 #ifndef PGN_EVAL_NO_GENZ_TUNING  // tools/evalbench sweeps the knob through the primary template instead
 template <int N>
 struct EvalTuning<genz::Oscillatory<N>> {
-  static constexpr int kMinBlocks = 4;
+  static constexpr int kMinBlocks = 5;  // 84 registers with the call-free point loop: 2.73e11 vs 2.70e11 at 4 (r02_evalbench_f.jsonl)
 };
 template <int N>
 struct EvalTuning<genz::ProductPeak<N>> {

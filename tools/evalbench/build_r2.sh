@@ -13,7 +13,7 @@ b() { # name include-dir family ndim flags...
   nvcc -I$inc -DBENCH_FAMILY=$fam -DBENCH_NDIM=$nd "$@" $common -o _build/r2_$name &
   n=$((n+1)); if [ $((n % 8)) = 0 ]; then wait; fi
 }
-for mb in 3 4 5; do
+for mb in 3 4 5 6; do
   b old_osc8_mb$mb _build/old_include Oscillatory 8 -DPGN_EVAL_MIN_BLOCKS=$mb
   b new_osc8_mb$mb $R/include Oscillatory 8 -DPGN_EVAL_MIN_BLOCKS=$mb "$@"
 done
