@@ -693,9 +693,30 @@ Engine::run_classify(double epsrel, int relerr)
       PGN_TRY(write_empty_stats(stats_dev_.as<double>(), stream_));
     err_cur_ = err_raw_.as<double>();
   } else if (parents_n_ > 0) {
-    ++launches_, k_classify<true><<<super_tiles_for(tiles_for(n_)), kBlock, 0, stream_>>>(
-      est_.as<double>(), err_raw_.as<double>(), par_est_[par_cur_].as<double>(),
-      err_ref_.as<double>(), active_.as<uint8_t>(), n_, epsrel, relerr, static_cast<unsigned int>(tiles_for(n_)), ts);
+    static const bool no_pairs = std::getenv("PGN_CLASSIFY_NO_PAIRS") != nullptr;
+    if (!no_pairs && n_ == 2 * parents_n_ && n_ >= kPairMinRegions) {
+      // sibling-pair kernel with TMA-staged loads (stages.cuh); its per-tile counts are atomics on a zeroed array
+      static bool attr_set = false;  // per process is enough: the attribute is set on every device it is used on below
+      int dev_now = -1;
+      if (!attr_set || cudaGetDevice(&dev_now) != cudaSuccess || dev_now != pairs_attr_device_) {
+        PGN_CUDA(cudaFuncSetAttribute(k_classify_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(kPairSmemBytes)));
+        attr_set = true;
+        pairs_attr_device_ = device_;
+      }
+      const unsigned int tiles = static_cast<unsigned int>(tiles_for(n_));
+      PGN_CUDA(cudaMemsetAsync(tile_count_.ptr, 0, sizeof(uint32_t) * tiles, stream_));
+      const size_t items = (parents_n_ + kTile - 1) / kTile;
+      const size_t cap = static_cast<size_t>(sm_count_) * 2;
+      ++launches_, k_classify_pairs<<<static_cast<unsigned int>(items < cap ? items : cap), kBlock, kPairSmemBytes,
+                                      stream_>>>(est_.as<double>(), err_raw_.as<double>(),
+                                                 par_est_[par_cur_].as<double>(), err_ref_.as<double>(),
+                                                 active_.as<uint8_t>(), n_, epsrel, relerr, tiles, ts);
+    } else {
+      ++launches_, k_classify<true><<<super_tiles_for(tiles_for(n_)), kBlock, 0, stream_>>>(
+        est_.as<double>(), err_raw_.as<double>(), par_est_[par_cur_].as<double>(), err_ref_.as<double>(),
+        active_.as<uint8_t>(), n_, epsrel, relerr, static_cast<unsigned int>(tiles_for(n_)), ts);
+    }
     err_cur_ = err_ref_.as<double>();
   } else {
     ++launches_, k_classify<false><<<super_tiles_for(tiles_for(n_)), kBlock, 0, stream_>>>(

@@ -186,17 +186,42 @@ finalize(const TileScratch& ts, unsigned int tiles, bool with_offsets, Acc* s_wa
   if (!s_last)
     return;
   __threadfence();
+  // This block runs alone at the end of the kernel: everything it reads comes from L2 at ~0.7 us per dependent
+  // round trip, so the loads of several records / count vectors are issued before the first use (the order of the
+  // merges, and with it every sum, is the same as in a plain loop).
   Acc a;
   acc_zero(a);
-  for (unsigned int b = threadIdx.x; b < parts; b += kBlock) {
-    const double* p = ts.partials + static_cast<size_t>(b) * kStatCount;
-    Acc t;
+  {
+    constexpr int kAhead = 4;
+    unsigned int b = threadIdx.x;
+    for (; b + (kAhead - 1) * kBlock < parts; b += kAhead * kBlock) {
+      double2 r[kAhead][4];  // a 64-byte record as four 16-byte loads
 #pragma unroll
-    for (int i = 0; i < 5; ++i)
-      t.v[i] = __ldcg(&p[i]);
-    t.mn = __ldcg(&p[kMinErr]);
-    t.mx = __ldcg(&p[kMaxErr]);
-    acc_merge(a, t);
+      for (int k = 0; k < kAhead; ++k) {
+        const double2* p = reinterpret_cast<const double2*>(ts.partials + static_cast<size_t>(b + k * kBlock) * kStatCount);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          r[k][q] = __ldcg(&p[q]);
+      }
+#pragma unroll
+      for (int k = 0; k < kAhead; ++k) {
+        Acc t;
+        t.v[0] = r[k][0].x, t.v[1] = r[k][0].y, t.v[2] = r[k][1].x, t.v[3] = r[k][1].y, t.v[4] = r[k][2].x;
+        t.mn = r[k][2].y;
+        t.mx = r[k][3].x;
+        acc_merge(a, t);
+      }
+    }
+    for (; b < parts; b += kBlock) {
+      const double* p = ts.partials + static_cast<size_t>(b) * kStatCount;
+      Acc t;
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+        t.v[i] = __ldcg(&p[i]);
+      t.mn = __ldcg(&p[kMinErr]);
+      t.mx = __ldcg(&p[kMaxErr]);
+      acc_merge(a, t);
+    }
   }
   a = block_reduce(a, s_warp);
   if (threadIdx.x == 0) {
@@ -212,25 +237,57 @@ finalize(const TileScratch& ts, unsigned int tiles, bool with_offsets, Acc* s_wa
     *ts.done = 0u;
   }
   if (with_offsets) {
-    const unsigned int chunk = (tiles + kBlock - 1) / kBlock;
-    const unsigned int lo = threadIdx.x * chunk;
+    // thread t owns the tiles [t * chunk, (t + 1) * chunk), chunk a multiple of four: counts travel as uint4
+    const unsigned int chunk = (((tiles + kBlock - 1) / kBlock) + 3u) & ~3u;
+    const unsigned int lo = threadIdx.x * chunk < tiles ? threadIdx.x * chunk : tiles;
     const unsigned int hi = lo + chunk < tiles ? lo + chunk : tiles;
+    const unsigned int hi4 = lo + ((hi - lo) & ~3u);  // whole vectors
     uint64_t local = 0;
-    for (unsigned int b = lo; b < hi; ++b)
-      local += __ldcg(&ts.tile_count[b]);
-    s_scan[threadIdx.x] = local;
-    __syncthreads();
-    // Hillis-Steele inclusive scan over the 256 chunk sums
-    for (int off = 1; off < kBlock; off <<= 1) {
-      const uint64_t add = threadIdx.x >= off ? s_scan[threadIdx.x - off] : 0;
-      __syncthreads();
-      s_scan[threadIdx.x] += add;
-      __syncthreads();
+    {
+      unsigned int b = lo;
+#pragma unroll 8
+      for (; b < hi4; b += 4) {
+        const uint4 c = __ldcg(reinterpret_cast<const uint4*>(ts.tile_count + b));
+        local += static_cast<uint64_t>(c.x) + c.y + c.z + c.w;
+      }
+      for (; b < hi; ++b)
+        local += __ldcg(&ts.tile_count[b]);
     }
-    uint64_t run = s_scan[threadIdx.x] - local;
-    for (unsigned int b = lo; b < hi; ++b) {
-      ts.tile_offset[b] = run;
-      run += __ldcg(&ts.tile_count[b]);
+    // inclusive scan over the 256 chunk sums: shuffles inside a warp, the eight warp totals through shared memory
+    uint64_t incl = local;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint64_t up = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off)
+        incl += up;
+    }
+    if (lane == 31)
+      s_scan[w] = incl;
+    __syncthreads();
+    uint64_t before = 0;
+#pragma unroll
+    for (int k = 0; k < kBlock / 32; ++k)
+      before += k < w ? s_scan[k] : 0;
+    uint64_t run = before + incl - local;
+    {
+      unsigned int b = lo;
+#pragma unroll 4
+      for (; b < hi4; b += 4) {
+        const uint4 c = __ldcg(reinterpret_cast<const uint4*>(ts.tile_count + b));
+        ulonglong2 o0, o1;
+        o0.x = run;
+        o0.y = o0.x + c.x;
+        o1.x = o0.y + c.y;
+        o1.y = o1.x + c.z;
+        run = o1.y + c.w;
+        reinterpret_cast<ulonglong2*>(ts.tile_offset + b)[0] = o0;
+        reinterpret_cast<ulonglong2*>(ts.tile_offset + b)[1] = o1;
+      }
+      for (; b < hi; ++b) {
+        ts.tile_offset[b] = run;
+        run += __ldcg(&ts.tile_count[b]);
+      }
     }
   }
   if (ts.box.nranks > 1) {
@@ -265,7 +322,7 @@ super_tiles_for(unsigned int tiles)
 #define PGN_CLASSIFY_MINBLOCKS 3
 #endif
 #ifndef PGN_CLASSIFY_DEPTH
-#define PGN_CLASSIFY_DEPTH 2
+#define PGN_CLASSIFY_DEPTH 3
 #endif
 template <bool REFINE>
 __global__ void __launch_bounds__(kBlock, PGN_CLASSIFY_MINBLOCKS)
@@ -293,22 +350,41 @@ k_classify(const double* __restrict__ est, const double* __restrict__ err_raw,
   dev::Acc a;
   dev::acc_zero(a);
   // The 16 rounds of a super-tile (256 regions each) run as a software pipeline of depth kDepth: the five loads of
-  // round r + kDepth are issued before the arithmetic of round r.
-  //
-  // Addressing: ncu showed this kernel bound by ISSUE SLOTS, not by HBM -- 140 instructions per region, 65 of them
-  // 64-bit index arithmetic (clamped region index, sibling = i +- n/2, parent = i mod n/2, five array addresses, per
-  // round).  A super-tile that exists completely and lies on one side of the list's midpoint (all but at most two)
-  // therefore takes the FAST path: five per-thread base pointers computed once, every access of the 16 rounds at a
-  // compile-time byte offset from them.
+  // round r + kDepth are issued before the arithmetic of round r, so a thread always has 5 * kDepth loads in flight
+  // while it computes (one correctly rounded FP64 division and seven accumulations per region: about as many FP64
+  // pipe cycles as the 29 bytes cost in HBM time -- a load-everything-then-compute loop pays both in turn).
   constexpr int kSteps = kSuper * kRounds;
   constexpr int kDepth = PGN_CLASSIFY_DEPTH;
   const size_t sbase = static_cast<size_t>(sup) * kSuper * kTile;
   struct Stage {
     double est, err, sib_est, sib_err, par;
   };
-  int my_active = 0, n_active = 0;
-  auto process = [&](const Stage& cur, bool exists, double* err_dst, uint8_t* flag_dst) {
-    if (exists) {
+  Stage st[kDepth];
+  auto load = [&](int step, Stage& s) {
+    size_t i = sbase + static_cast<size_t>(step) * kBlock + threadIdx.x;
+    i = i < n ? i : n - 1;  // clamped: the loads are unconditional
+    s.est = est[i];
+    s.err = err_raw[i];
+    if constexpr (REFINE) {
+      const bool right = (i + i) >= n;
+      const size_t sib = right ? i - half : i + half;
+      const size_t par = right ? i - half : i;
+      s.sib_est = est[sib];
+      s.sib_err = err_raw[sib];
+      s.par = parent_est[par];
+    }
+  };
+#pragma unroll
+  for (int d = 0; d < kDepth; ++d)
+    load(d, st[d]);
+  int my_active = 0;
+#pragma unroll
+  for (int step = 0; step < kSteps; ++step) {
+    const Stage cur = st[step % kDepth];
+    if (step + kDepth < kSteps)
+      load(step + kDepth, st[step % kDepth]);
+    const size_t i = sbase + static_cast<size_t>(step) * kBlock + threadIdx.x;
+    if (i < n) {
       const double self_est = cur.est;
       double e = cur.err;
       double flag = 1.0;
@@ -321,102 +397,250 @@ k_classify(const double* __restrict__ est, const double* __restrict__ err_raw,
           e = __dmul_rn(e, c);
         }
         e = __dadd_rn(diff, e);
-        *err_dst = e;
+        err_out[i] = e;
         if (relerr_classification) {
-          // fmax(epsrel * |est|, 1e-200) without the library's NaN plumbing (a NaN product selects 1e-200 either way)
-          const double t = __dmul_rn(epsrel, fabs(self_est));
-          const double tol = t > 1e-200 ? t : 1e-200;
+          const double tol = fmax(__dmul_rn(epsrel, fabs(self_est)), 1e-200);
           flag = (e < tol) ? 0.0 : 1.0;
         }
       }
-      *flag_dst = flag != 0.0 ? 1 : 0;
+      active[i] = flag != 0.0 ? 1 : 0;
       my_active += flag != 0.0 ? 1 : 0;
       a.v[kSumEst] += self_est;
       a.v[kSumErr] += e;
       a.v[kSumActEst] += flag * self_est;  // thrust::inner_product(flags, estimates)
       a.v[kSumActErr] += flag * e;
-      // (the count of active regions is kept as an integer, n_active, and converted once: sums of 1.0 are exact)
-      // min / max as compare-and-select: a NaN error leaves both untouched, like fmin / fmax
-      a.mn = e < a.mn ? e : a.mn;
-      a.mx = e > a.mx ? e : a.mx;
+      a.v[kNumActive] += flag;
+      a.mn = fmin(a.mn, e);
+      a.mx = fmax(a.mx, e);
     }
-  };
-  auto end_of_round = [&](int step) {
     if ((step % kRounds) == kRounds - 1) {
       // active regions of the tile just finished: warp sums into a shared counter (integers: order does not matter)
       const int warp_active = __reduce_add_sync(0xffffffffu, my_active);
       if ((threadIdx.x & 31) == 0 && warp_active)
         atomicAdd(&s_tile_active[step / kRounds], static_cast<unsigned int>(warp_active));
-      n_active += my_active;
       my_active = 0;
     }
-  };
-  const size_t send = sbase + static_cast<size_t>(kSuper) * kTile;  // one past the super-tile
-  const bool whole = send <= n;
-  const bool one_side = !REFINE || send <= half || sbase >= half;
-  if (whole && one_side) {  // block-uniform
-    const double* p_est = est + sbase + threadIdx.x;
-    const double* p_err = err_raw + sbase + threadIdx.x;
-    const double* p_sib_est = p_est;
-    const double* p_sib_err = p_err;
-    const double* p_par = nullptr;
-    double* p_out = REFINE ? err_out + sbase + threadIdx.x : nullptr;
-    uint8_t* p_flag = active + sbase + threadIdx.x;
-    if constexpr (REFINE) {
-      const bool right = sbase >= half;
-      p_sib_est = right ? p_est - half : p_est + half;
-      p_sib_err = right ? p_err - half : p_err + half;
-      p_par = parent_est + (right ? sbase - half : sbase) + threadIdx.x;
-    }
-    Stage st[kDepth];
-    auto load = [&](int step, Stage& s) {
-      s.est = p_est[step * kBlock];
-      s.err = p_err[step * kBlock];
-      if constexpr (REFINE) {
-        s.sib_est = p_sib_est[step * kBlock];
-        s.sib_err = p_sib_err[step * kBlock];
-        s.par = p_par[step * kBlock];
-      }
-    };
-#pragma unroll
-    for (int d = 0; d < kDepth; ++d)
-      load(d, st[d]);
-#pragma unroll
-    for (int step = 0; step < kSteps; ++step) {
-      const Stage cur = st[step % kDepth];
-      if (step + kDepth < kSteps)
-        load(step + kDepth, st[step % kDepth]);
-      process(cur, true, p_out + step * kBlock, p_flag + step * kBlock);
-      end_of_round(step);
-    }
-  } else {
-    // generic path (the last super-tile and the one that straddles the midpoint): clamped 64-bit indices
-#pragma unroll 1
-    for (int step = 0; step < kSteps; ++step) {
-      const size_t i0 = sbase + static_cast<size_t>(step) * kBlock + threadIdx.x;
-      const size_t i = i0 < n ? i0 : n - 1;
-      Stage cur;
-      cur.est = est[i];
-      cur.err = err_raw[i];
-      if constexpr (REFINE) {
-        const bool right = (i + i) >= n;
-        const size_t sib = right ? i - half : i + half;
-        const size_t par = right ? i - half : i;
-        cur.sib_est = est[sib];
-        cur.sib_err = err_raw[sib];
-        cur.par = parent_est[par];
-      }
-      process(cur, i0 < n, REFINE ? err_out + i : nullptr, active + i);
-      end_of_round(step);
-    }
   }
-  a.v[kNumActive] = static_cast<double>(n_active);
   __syncthreads();
   if (threadIdx.x < kSuper && sup * kSuper + threadIdx.x < tiles)
     ts.tile_count[sup * kSuper + threadIdx.x] = s_tile_active[threadIdx.x];
   a = dev::block_reduce(a, s_warp);
   if (threadIdx.x == 0) {
     double* p = ts.partials + static_cast<size_t>(sup) * kStatCount;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+      p[i] = a.v[i];
+    p[kMinErr] = a.mn;
+    p[kMaxErr] = a.mx;
+  }
+  dev::finalize(ts, tiles, true, s_warp, s_scan, gridDim.x);
+}
+
+// ---- classify, sibling-pair form with TMA-staged loads -------------------------------------------------------------
+// The children of parent j sit at j (left half of the list) and j + n/2 (right half): the two refinements read the
+// same five numbers -- both estimates, both raw errors, the parent estimate -- and share |est_l + est_r - parent| / 4,
+// err_l + err_r and the correction factor (additions commute, so each twin obtains bit for bit what the one-region
+// form computes).  A work item is therefore 1024 PAIRS: est/err of [b, b+1024) and of [b + n/2, b + n/2 + 1024) plus
+// parent[b, b+1024) -- every input byte is fetched exactly once (20 B per region instead of 40 through L2) and a pair
+// costs one correctly rounded division instead of two.
+// The five 8 KB row segments of an item arrive by 1-D bulk copies (cp.async.bulk, the TMA engine) into one of two
+// shared-memory stages, completion on an mbarrier: the copies of item k+1 (and k+2) are in flight while item k is
+// computed, without holding a register, so the 128-register budget goes to the arithmetic and two resident blocks per
+// SM keep ~160 KB of loads in flight (HBM needs ~45 KB per SM).  Persistent grid; one partial record per BLOCK (the
+// item -> block map is static, so the sums stay run-to-run deterministic); per-tile active counts by integer atomics
+// into tile_count, which the host zeroes before the launch (the right-hand rows straddle two tiles).
+// A right-hand row starts at an odd element when n/2 is odd: the copy then starts one element earlier (16-byte
+// aligned) and the consumers index one element further.  The last item, when shorter than 1024 pairs, is read with
+// plain loads.
+constexpr int kPairRow = kTile + 2;           // doubles per staged row (room for the alignment shift)
+constexpr int kPairStage = 5 * kPairRow;      // est_l, err_l, parent, est_r, err_r
+constexpr size_t kPairSmemBytes = sizeof(double) * 2 * kPairStage + 2 * sizeof(unsigned long long);
+constexpr size_t kPairMinRegions = 128 * 1024;  // below this the one-region kernel is used
+
+namespace dev {
+__device__ __forceinline__ uint32_t
+smem_addr(const void* p)
+{
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void
+mbar_init(unsigned long long* bar, unsigned int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void
+mbar_expect_tx(unsigned long long* bar, unsigned int bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void
+mbar_wait(unsigned long long* bar, unsigned int parity)
+{
+  asm volatile(
+    "{\n"
+    ".reg .pred p;\n"
+    "PGN_WAIT:\n"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+    "@p bra PGN_DONE;\n"
+    "bra PGN_WAIT;\n"
+    "PGN_DONE:\n"
+    "}\n" ::"r"(smem_addr(bar)),
+    "r"(parity)
+    : "memory");
+}
+// global -> shared bulk copy (bytes and both addresses multiples of 16), completion counted on `bar`
+__device__ __forceinline__ void
+bulk_load(void* dst, const void* src, unsigned int bytes, unsigned long long* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                 smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+}  // namespace dev
+
+__global__ void __launch_bounds__(kBlock, 2)
+k_classify_pairs(const double* __restrict__ est, const double* __restrict__ err_raw,
+                 const double* __restrict__ parent_est, double* __restrict__ err_out,
+                 uint8_t* __restrict__ active, size_t n, double epsrel, int relerr_classification,
+                 unsigned int tiles, TileScratch ts)
+{
+  extern __shared__ __align__(128) unsigned char pair_smem[];
+  double* stage = reinterpret_cast<double*>(pair_smem);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(pair_smem + sizeof(double) * 2 * kPairStage);
+  __shared__ dev::Acc s_warp[kBlock / 32];
+  __shared__ uint64_t s_scan[kBlock];
+
+  const size_t half = n >> 1;  // n is even (host-checked)
+  const unsigned int items = static_cast<unsigned int>((half + kTile - 1) / kTile);
+  const unsigned int shift = static_cast<unsigned int>(half & 1);  // right-hand rows start `shift` elements into their stage row
+  auto item_len = [&](unsigned int it) -> unsigned int {
+    const size_t b = static_cast<size_t>(it) * kTile;
+    return static_cast<unsigned int>(half - b < kTile ? half - b : kTile);
+  };
+  // thread 0: arm the stage's barrier and start the five copies of item `it` (only whole items travel this way)
+  auto issue = [&](unsigned int it, int s) {
+    const size_t b = static_cast<size_t>(it) * kTile;
+    double* dst = stage + s * kPairStage;
+    const unsigned int row = sizeof(double) * kTile, rrow = sizeof(double) * (kTile + 2 * shift);
+    dev::mbar_expect_tx(&full[s], 3 * row + 2 * rrow);
+    dev::bulk_load(dst, est + b, row, &full[s]);
+    dev::bulk_load(dst + kPairRow, err_raw + b, row, &full[s]);
+    dev::bulk_load(dst + 2 * kPairRow, parent_est + b, row, &full[s]);
+    dev::bulk_load(dst + 3 * kPairRow, est + b + half - shift, rrow, &full[s]);
+    dev::bulk_load(dst + 4 * kPairRow, err_raw + b + half - shift, rrow, &full[s]);
+  };
+  if (threadIdx.x == 0) {
+    dev::mbar_init(&full[0], 1);
+    dev::mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int i0 = blockIdx.x, i1 = blockIdx.x + gridDim.x;
+    if (i0 < items && item_len(i0) == kTile)
+      issue(i0, 0);
+    if (i1 < items && item_len(i1) == kTile)
+      issue(i1, 1);
+  }
+
+  dev::Acc a;
+  dev::acc_zero(a);
+  int n_active = 0;
+  const int lane = threadIdx.x & 31;
+  unsigned int k = 0;
+  for (unsigned int it = blockIdx.x; it < items; it += gridDim.x, ++k) {
+    const int s = static_cast<int>(k & 1u);
+    const size_t b = static_cast<size_t>(it) * kTile;
+    const unsigned int len = item_len(it);
+    const bool staged = len == kTile;
+    const double* row = stage + s * kPairStage;
+    if (staged)
+      dev::mbar_wait(&full[s], (k >> 1) & 1u);
+    int cnt_l = 0, cnt_r0 = 0, cnt_r1 = 0;
+    const size_t r_base = b + half;
+    const size_t r_split = ((r_base >> 10) + 1) << 10;  // first region of the right-hand row's second tile
+#pragma unroll
+    for (int q = 0; q < kRounds; ++q) {
+      const unsigned int j = q * kBlock + threadIdx.x;
+      if (j < len) {
+        double est_l, err_l, par, est_r, err_r;
+        if (staged) {
+          est_l = row[j];
+          err_l = row[kPairRow + j];
+          par = row[2 * kPairRow + j];
+          est_r = row[3 * kPairRow + shift + j];
+          err_r = row[4 * kPairRow + shift + j];
+        } else {
+          est_l = est[b + j];
+          err_l = err_raw[b + j];
+          par = parent_est[b + j];
+          est_r = est[r_base + j];
+          err_r = err_raw[r_base + j];
+        }
+        // Phases.cuh:251-261 with the rounding sequence of the reference's machine code (see k_classify)
+        const double diff = fabs(__dmul_rn(__dsub_rn(__dadd_rn(est_l, est_r), par), 0.25));
+        const double both = __dadd_rn(err_l, err_r);
+        double e_l = err_l, e_r = err_r;
+        if (both > 0.0) {
+          const double c = __dadd_rn(__ddiv_rn(__dadd_rn(diff, diff), both), 1.0);
+          e_l = __dmul_rn(e_l, c);
+          e_r = __dmul_rn(e_r, c);
+        }
+        e_l = __dadd_rn(diff, e_l);
+        e_r = __dadd_rn(diff, e_r);
+        err_out[b + j] = e_l;
+        err_out[r_base + j] = e_r;
+        double flag_l = 1.0, flag_r = 1.0;
+        if (relerr_classification) {
+          flag_l = (e_l < fmax(__dmul_rn(epsrel, fabs(est_l)), 1e-200)) ? 0.0 : 1.0;
+          flag_r = (e_r < fmax(__dmul_rn(epsrel, fabs(est_r)), 1e-200)) ? 0.0 : 1.0;
+        }
+        active[b + j] = flag_l != 0.0 ? 1 : 0;
+        active[r_base + j] = flag_r != 0.0 ? 1 : 0;
+        cnt_l += flag_l != 0.0 ? 1 : 0;
+        if (r_base + j < r_split)
+          cnt_r0 += flag_r != 0.0 ? 1 : 0;
+        else
+          cnt_r1 += flag_r != 0.0 ? 1 : 0;
+        a.v[kSumEst] += est_l;
+        a.v[kSumErr] += e_l;
+        a.v[kSumActEst] += flag_l * est_l;
+        a.v[kSumActErr] += flag_l * e_l;
+        a.mn = fmin(a.mn, e_l);
+        a.mx = fmax(a.mx, e_l);
+        a.v[kSumEst] += est_r;
+        a.v[kSumErr] += e_r;
+        a.v[kSumActEst] += flag_r * est_r;
+        a.v[kSumActErr] += flag_r * e_r;
+        a.mn = fmin(a.mn, e_r);
+        a.mx = fmax(a.mx, e_r);
+      }
+    }
+    n_active += cnt_l + cnt_r0 + cnt_r1;
+    // active regions per tile of the list (what compaction needs): integer atomics, the order does not matter
+    cnt_l = __reduce_add_sync(0xffffffffu, cnt_l);
+    cnt_r0 = __reduce_add_sync(0xffffffffu, cnt_r0);
+    cnt_r1 = __reduce_add_sync(0xffffffffu, cnt_r1);
+    if (lane == 0) {
+      if (cnt_l)
+        atomicAdd(&ts.tile_count[b >> 10], static_cast<unsigned int>(cnt_l));
+      if (cnt_r0)
+        atomicAdd(&ts.tile_count[r_base >> 10], static_cast<unsigned int>(cnt_r0));
+      if (cnt_r1)
+        atomicAdd(&ts.tile_count[(r_base >> 10) + 1], static_cast<unsigned int>(cnt_r1));
+    }
+    __syncthreads();  // every thread has read stage s
+    if (threadIdx.x == 0) {
+      const unsigned int nxt = it + 2 * gridDim.x;
+      if (nxt < items && item_len(nxt) == kTile)
+        issue(nxt, s);
+    }
+  }
+  a.v[kNumActive] = static_cast<double>(n_active);
+  a = dev::block_reduce(a, s_warp);
+  if (threadIdx.x == 0) {
+    double* p = ts.partials + static_cast<size_t>(blockIdx.x) * kStatCount;
 #pragma unroll
     for (int i = 0; i < 5; ++i)
       p[i] = a.v[i];

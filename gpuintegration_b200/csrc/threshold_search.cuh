@@ -90,6 +90,10 @@ scaled_mantissa(unsigned long long bits, int eref)
 __device__ __forceinline__ double
 integer_sum_to_double(unsigned long long lo, unsigned long long hi, int eref)
 {
+  // lo collects 32-bit pieces and passes 2^53 on long lists: carry its upper half into hi in integers first, so that
+  // both conversions are exact (hi < 2^46 for 2^24 elements, lo < 2^32) and the FMA is the only rounding
+  hi += lo >> 32;
+  lo &= 0xffffffffull;
   const double v = __fma_rn(static_cast<double>(hi), 4294967296.0, static_cast<double>(lo));
   return scalbn(v, eref - 1075);
 }

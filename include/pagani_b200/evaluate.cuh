@@ -63,6 +63,24 @@ constexpr int kWarpsPerBlock = PGN_EVAL_WARPS;
 #define PGN_EVAL_PIPELINE 0
 #endif
 
+// 1: the middle trips run as compile-time segments (TripPlan: one copy of the trip body per run of trips that share
+// a generator set, weights as constant-bank operands, no per-trip set lookup); 0: one loop over all middle trips.
+// Measured on B200 (profiles/r02_evalbench_h.jsonl): the segments save 14 of 134 instructions per trip but multiply
+// the code size by the number of runs -- +4 % for the 10-D C0 family (41 trips, long runs, small body), -2 % for
+// F_1_8D, -27 % for the Gaussian (its pow(x, 2.) body is ~1300 instructions: seven copies no longer fit the
+// instruction cache).  Off by default; a functor opts in through EvalTuning<F>::kSegments.
+#ifndef PGN_EVAL_SEGMENTS
+#define PGN_EVAL_SEGMENTS 0
+#endif
+
+// 1: a last trip none of whose chain-B points exists (8-D: 17 points) evaluates chain A only
+#ifndef PGN_EVAL_TAIL_A_ONLY
+#define PGN_EVAL_TAIL_A_ONLY 1
+#endif
+#ifndef PGN_EVAL_PREFETCH_BOUNDS
+#define PGN_EVAL_PREFETCH_BOUNDS 1
+#endif
+
 // Launch-bound tuning knob of the evaluation kernel: resident 128-thread blocks per SM the register
 // allocation must allow (4 -> up to 128 registers per thread, 7 -> 72, 8 -> 64).  Cheap integrands
 // want registers (the point loop is latency bound), pow()-heavy ones want warps.  Specialise for a
@@ -70,7 +88,14 @@ constexpr int kWarpsPerBlock = PGN_EVAL_WARPS;
 template <typename F>
 struct EvalTuning {
   static constexpr int kMinBlocks = PGN_EVAL_MIN_BLOCKS;
+  static constexpr bool kSegments = PGN_EVAL_SEGMENTS != 0;
 };
+// kSegments of a specialisation that does not declare it: the default
+template <typename F, class = void>
+struct eval_segments : std::integral_constant<bool, PGN_EVAL_SEGMENTS != 0> {};
+template <typename F>
+struct eval_segments<F, std::void_t<decltype(EvalTuning<F>::kSegments)>>
+  : std::integral_constant<bool, EvalTuning<F>::kSegments> {};
 constexpr int kWeightRow = 6;  // 5 rule weights padded to 48 B so a row is three 16-byte loads
 
 // values of pgn_region_view::reserved
@@ -544,6 +569,55 @@ struct BpLayout {
   }
 };
 
+// Compile-time plan of the trips 1 .. kTrips-2 of a region (all 64 points exist): maximal runs of consecutive trips
+// whose points belong to ONE generator set (the rule weights are then compile-time constant-bank operands of the
+// accumulating FMAs and the loop over the run carries no set bookkeeping at all), separated by runs of trips that
+// straddle a set boundary (per-lane weights).  8-D: mixed {1,2}, set 6 x3, mixed {6}, set 7 x6, mixed {13}, set 8 x3.
+template <int NDIM>
+struct TripPlan {
+  static constexpr int kFeval = feval_of(NDIM);
+  static constexpr int kTrips = (kFeval + 63) / 64;
+  static constexpr int kCap = kTrips > 2 ? kTrips : 2;
+  int nseg = 0;
+  int first[kCap] = {};
+  int count[kCap] = {};
+  int set[kCap] = {};  // generator set of the run, -1: mixed
+  static constexpr int
+  set_of(int p)
+  {
+    int st = 0;
+    for (int k = 1; k < PGN_NSETS; ++k)
+      st += p >= set_begin(NDIM, k) ? 1 : 0;
+    return st;
+  }
+  constexpr TripPlan()
+  {
+    for (int t = 1; t <= kTrips - 2; ++t) {
+      const int s0 = set_of(64 * t), s1 = set_of(64 * t + 63);
+      const int st = s0 == s1 ? s0 : -1;
+      if (nseg > 0 && set[nseg - 1] == st) {
+        ++count[nseg - 1];
+      } else {
+        first[nseg] = t;
+        count[nseg] = 1;
+        set[nseg] = st;
+        ++nseg;
+      }
+    }
+  }
+};
+
+template <int NDIM>
+inline constexpr TripPlan<NDIM> kTripPlan{};
+
+// fn(std::integral_constant<int, 0>{}), fn(std::integral_constant<int, 1>{}), ...
+template <class Fn, int... I>
+__device__ __forceinline__ void
+for_constexpr(Fn&& fn, std::integer_sequence<int, I...>)
+{
+  (fn(std::integral_constant<int, I>{}), ...);
+}
+
 template <int IMM>
 __device__ __forceinline__ double
 lds_f64(uint32_t addr)
@@ -744,8 +818,9 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
   // The bounds of the NEXT region of this warp are loaded while the current one is evaluated: the two global loads
   // (HBM / L2 latency, several hundred cycles) are the only long-latency operations of a region, and with four to
   // five warps per scheduler a warp waiting for them at the top of every region costs issue slots.
+  // (PGN_EVAL_PREFETCH_BOUNDS=0 loads them at the top of the region instead: four registers fewer across the loop.)
   double next_lo = 0.0, next_len = 0.0;
-  {
+  if constexpr (PGN_EVAL_PREFETCH_BOUNDS) {
     const size_t first = static_cast<size_t>(blockIdx.x) * kWarpsPerBlock + warp;
     if (first < n)
       load_bounds<NDIM>(P, first, lane, next_lo, next_len);
@@ -754,9 +829,13 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
     __syncwarp();
     double vol;
     int max_dim;
+    if constexpr (!PGN_EVAL_PREFETCH_BOUNDS)
+      load_bounds<NDIM>(P, reg, lane, next_lo, next_len);
     region_prologue<NDIM>(P, next_lo, next_len, lane, s_tp, s_tm, s_lo, s_up, s_ext, s_x, vol, max_dim);
-    if (reg + stride < n)
-      load_bounds<NDIM>(P, reg + stride, lane, next_lo, next_len);
+    if constexpr (PGN_EVAL_PREFETCH_BOUNDS) {
+      if (reg + stride < n)
+        load_bounds<NDIM>(P, reg + stride, lane, next_lo, next_len);
+    }
 
     double sa[PGN_NRULES], sb[PGN_NRULES];
 #pragma unroll
@@ -780,6 +859,20 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
       }
       BpGather<NDIM, 0>::run(ca, xbase, x[0]);
       BpGather<NDIM, 0>::run(cb, xbase, x[1]);
+    };
+    // coordinates of the lane's chain-A point of trip t only
+    auto gather_a = [&](double (&xa)[NDIM], int t) {
+      constexpr int kPointBytes = L::kCodeWords * 4;
+      const uint32_t a = lane_codes + static_cast<uint32_t>(t) * (64u * kPointBytes);
+      Words4 ca;
+      if constexpr (L::kCodeWords == 2) {
+        const uint2 va = lds_u32x2<0>(a);
+        ca = Words4{va.x, va.y, 0u, 0u};
+      } else {
+        const uint4 va = lds_u32x4<0>(a);
+        ca = Words4{va.x, va.y, va.z, va.w};
+      }
+      BpGather<NDIM, 0>::run(ca, xbase, xa);
     };
     // f(x) * Jacobian of both points
     auto values = [&](const double (&x)[2][NDIM], double (&f)[2]) {
@@ -877,14 +970,53 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
       gather(x, 0);
       ragged_trip(x, 0, true);
       if constexpr (kTrips >= 2) {
+        if constexpr (eval_segments<F>::value) {
+        // trips 1 .. kTrips-2 as compile-time runs (TripPlan): inside a single-set run the five weights are
+        // constant-bank operands and a trip is gather + values + 10 FMAs, nothing else
+        auto segment = [&](auto sc) {
+          constexpr int S = decltype(sc)::value;
+          constexpr int kFirst = kTripPlan<NDIM>.first[S], kCount = kTripPlan<NDIM>.count[S];
+          constexpr int kSet = kTripPlan<NDIM>.set[S];
 #pragma unroll 1
-        for (int t = 1; t <= kMiddle; ++t) {
-          gather(x, t);
-          middle_trip(x, t);
+          for (int t = kFirst; t < kFirst + kCount; ++t) {
+            gather(x, t);
+            double f[2];
+            values(x, f);
+            if constexpr (kSet >= 0) {
+              accumulate(sa, f[0], P.wc + kSet * PGN_NRULES);
+              accumulate(sb, f[1], P.wc + kSet * PGN_NRULES);
+            } else {
+              const int pa = (t << 6) + lane;
+              accumulate(sa, f[0], lane_weights(t << 6, pa));
+              accumulate(sb, f[1], lane_weights((t << 6) + 32, pa + 32));
+            }
+          }
+        };
+        for_constexpr(segment, std::make_integer_sequence<int, kTripPlan<NDIM>.nseg>{});
+        } else {
+#pragma unroll 1
+          for (int t = 1; t <= kMiddle; ++t) {
+            gather(x, t);
+            middle_trip(x, t);
+          }
         }
         // last trip (Sample.cuh:238-252): only some of its points exist
-        gather(x, kTrips - 1);
-        ragged_trip(x, kTrips - 1, false);
+        constexpr int kTail = kFeval - 64 * (kTrips - 1);
+        if constexpr (PGN_EVAL_TAIL_A_ONLY && kTail <= 32) {
+          // none of the points 64 (kTrips-1) + 32 + lane exists: chain B is complete, only chain A has a last term
+          double xa[1][NDIM], fv[1];
+          gather_a(xa[0], kTrips - 1);
+          if constexpr (has_batch_fast<F, NDIM, 1>::value)
+            exact = static_cast<const F*>(fptr)->template batch_fast<1>(xa, fv) && exact;
+          else
+            BatchCall<F, NDIM, 1>::run(fptr, xa, fv);
+          const int pa = ((kTrips - 1) << 6) + lane;
+          if (pa < kFeval)
+            accumulate(sa, __dmul_rn(fv[0], jac), lane_weights((kTrips - 1) << 6, pa));
+        } else {
+          gather(x, kTrips - 1);
+          ragged_trip(x, kTrips - 1, false);
+        }
       }
     }
 #endif

@@ -430,6 +430,11 @@ struct EvalTuning<genz::ProductPeak<N>> {
   static constexpr int kMinBlocks = PGN_GENZ_FAST_POW ? 4 : 8;
 };
 template <int N>
+struct EvalTuning<genz::CZero<N>> {
+  static constexpr int kMinBlocks = 4;     // the primary template's default
+  static constexpr bool kSegments = true;  // +4 % at 10-D (r02_evalbench_h.jsonl)
+};
+template <int N>
 struct EvalTuning<genz::CornerPeak<N>> {
   static constexpr int kMinBlocks = 8;
 };
