@@ -696,12 +696,9 @@ Engine::run_classify(double epsrel, int relerr)
     static const bool no_pairs = std::getenv("PGN_CLASSIFY_NO_PAIRS") != nullptr;
     if (!no_pairs && n_ == 2 * parents_n_ && n_ >= kPairMinRegions) {
       // sibling-pair kernel with TMA-staged loads (stages.cuh); its per-tile counts are atomics on a zeroed array
-      static bool attr_set = false;  // per process is enough: the attribute is set on every device it is used on below
-      int dev_now = -1;
-      if (!attr_set || cudaGetDevice(&dev_now) != cudaSuccess || dev_now != pairs_attr_device_) {
+      if (pairs_attr_device_ != device_) {  // the attribute is per device: once per engine is enough
         PGN_CUDA(cudaFuncSetAttribute(k_classify_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(kPairSmemBytes)));
-        attr_set = true;
         pairs_attr_device_ = device_;
       }
       const unsigned int tiles = static_cast<unsigned int>(tiles_for(n_));
@@ -880,6 +877,12 @@ Engine::heuristic_classify_stage(double epsrel, double last_estimate, double ite
   PGN_TRY(agree_mem_capacity());
   HeuristicOutcome hs;
   PGN_TRY(heuristic_classify(n_, 0.0, iter_errorest, iter_finished_errorest, total_finished_errorest, &hs, true));
+  if (!hs.success) {
+    // The flags are still those of classify(), but the host-driven search leaves the count of its last PROBE in the
+    // statistics slot filter() sizes its output from: recount from the flags.
+    PGN_TRY(run_recount());
+    PGN_TRY(sync_stats(false));
+  }
   std::memset(out, 0, sizeof *out);
   out->success = hs.success ? 1 : 0;
   out->must_terminate = hs.must_terminate ? 1 : 0;
@@ -1403,10 +1406,10 @@ k_outside_to_double(const unsigned long long* outside, double* out)
 }
 }  // namespace
 
-int
-Engine::prepare_search(const BucketPlan& plan, BucketTables* T)
+namespace {
+void
+lay_out_tables(unsigned long long* base, BucketTables* T)
 {
-  unsigned long long* base = search_tab_.as<unsigned long long>();
   const size_t nbm = kMaxBuckets;
   T->count = base;
   T->start = base + nbm;               // nbm + 1
@@ -1417,6 +1420,17 @@ Engine::prepare_search(const BucketPlan& plan, BucketTables* T)
   T->outside = base + 6 * nbm + 3;
   T->acc_lo = base + 6 * nbm + 8;
   T->acc_hi = base + 7 * nbm + 8;
+  T->sorted = nullptr;
+}
+}  // namespace
+
+// T: this rank's partition.  G (several ranks with peer mailboxes, else null): the tables of the concatenated list,
+// from ONE all-reduce of the counts and integer bucket sums (threshold_search.cuh, k_tables_to_double).
+int
+Engine::prepare_search(const BucketPlan& plan, BucketTables* T, BucketTables* G)
+{
+  const size_t nbm = kMaxBuckets;
+  lay_out_tables(search_tab_.as<unsigned long long>(), T);
   PGN_TRY(sorted_err_.reserve(sizeof(double) * std::max<size_t>(n_, 1)));
   T->sorted = sorted_err_.as<double>();
   PGN_CUDA(cudaMemsetAsync(search_tab_.ptr, 0, 8 * (8 * nbm + 8), stream_));
@@ -1431,7 +1445,17 @@ Engine::prepare_search(const BucketPlan& plan, BucketTables* T)
                                                                      static_cast<size_t>(sm_count_) * 8));
     ++launches_, k_bucket_sums<<<sum_grid, kSumThreads, 0, stream_>>>(plan, *T);
   }
-  ++launches_, k_bucket_suffix<<<1, kSearchBlock, 0, stream_>>>(plan, *T);
+  if (G) {
+    PGN_TRY(search_gtab_.reserve(8 * (8 * nbm + 8)));
+    PGN_TRY(search_gd_.reserve(sizeof(double) * (3 * nbm + 8)));
+    lay_out_tables(search_gtab_.as<unsigned long long>(), G);
+    ++launches_, k_tables_to_double<<<1, kSearchBlock, 0, stream_>>>(plan, *T, search_gd_.as<double>());
+    PGN_CUDA(cudaGetLastError());
+    PGN_TRY(comm_->allreduce(search_gd_.as<double>(), static_cast<int>(3 * plan.nb + 1), kOpSum, stream_));
+    ++launches_, k_global_tables<<<1, kSearchBlock, 0, stream_>>>(plan, search_gd_.as<double>(), *G);
+  } else {
+    ++launches_, k_bucket_suffix<<<1, kSearchBlock, 0, stream_>>>(plan, *T);
+  }
   PGN_CUDA(cudaGetLastError());
   return PGN_OK;
 }
@@ -1532,10 +1556,10 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
   // Device-side search: partition the errors into value buckets once, then either run the whole
   // bisection in one kernel (single rank) or answer every probe from the tables (several ranks).
   BucketPlan plan;
-  BucketTables tables;
+  BucketTables tables, global_tables;
   bool fast = device_search_ && make_bucket_plan(min_err, max_err, &plan);
   if (fast)
-    PGN_TRY(prepare_search(plan, &tables));
+    PGN_TRY(prepare_search(plan, &tables, multi && peer_ready_ ? &global_tables : nullptr));
   bool searched = false;
   if (fast && (!multi || peer_ready_)) {
     SearchIO* h = static_cast<SearchIO*>(host_search_);
@@ -1558,13 +1582,15 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
       fill_peer_box(&box, 4000000000ll);  // ~2 s of SM clocks: the ranks run this kernel in lock step
     PGN_CUDA(cudaMemcpyAsync(search_io_.ptr, h, sizeof *h, cudaMemcpyHostToDevice, stream_));
     if (multi)
-      ++launches_, k_search<true><<<1, kSearchBlock, 0, stream_>>>(plan, tables, search_io_.as<SearchIO>(), box);
+      ++launches_, k_search<true><<<1, kSearchBlock, 0, stream_>>>(plan, tables, global_tables,
+                                                                      search_io_.as<SearchIO>(), box);
     else
-      ++launches_, k_search<false><<<1, kSearchBlock, 0, stream_>>>(plan, tables, search_io_.as<SearchIO>(), box);
+      ++launches_, k_search<false><<<1, kSearchBlock, 0, stream_>>>(plan, tables, tables, search_io_.as<SearchIO>(),
+                                                                       box);
     PGN_CUDA(cudaGetLastError());
     PGN_CUDA(cudaMemcpyAsync(h, search_io_.ptr, sizeof *h, cudaMemcpyDeviceToHost, stream_));
-    PGN_CUDA(cudaMemcpyAsync(h_outside, tables.outside, sizeof *h_outside, cudaMemcpyDeviceToHost,
-                             stream_));
+    PGN_CUDA(cudaMemcpyAsync(h_outside, multi ? global_tables.outside : tables.outside, sizeof *h_outside,
+                             cudaMemcpyDeviceToHost, stream_));
     PGN_CUDA(cudaStreamSynchronize(stream_));
     if (multi)
       peer_seq_ = h->seq_base;
@@ -1582,6 +1608,9 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
       pass_mem = h->pass_mem != 0;
       pass_budget = h->pass_budget != 0;
       out->probes += h->probes;
+      if (search_debug)
+        std::fprintf(stderr, "[pgn device search] probes=%d computed=%d peer exchanges=%d\n", h->probes,
+                     h->probes_computed, h->exchanges);
     } else {
       fast = false;  // NaN / inf / negative errors: keep the reference's flag*err semantics exactly
     }

@@ -138,7 +138,7 @@ private:
   int heuristic_classify(size_t n_global, double iter_est, double iter_err, double fin_err,
                          double cum_err, HeuristicOutcome* out, bool force = false);
   // bucket partition of the current errors for the device-side threshold search
-  int prepare_search(const struct BucketPlan& plan, struct BucketTables* tables);
+  int prepare_search(const struct BucketPlan& plan, struct BucketTables* tables, struct BucketTables* global);
   double mem_capacity_bytes() const;  // this rank's figure
   int agree_mem_capacity();            // -> mem_capacity_, identical on every rank
   double mem_capacity_ = 16e9;
@@ -187,6 +187,7 @@ private:
   DeviceBuf pack_send_, pack_recv_;
   // heuristic threshold search: errors grouped by value bucket, bucket tables, search in/out block
   DeviceBuf sorted_err_, search_tab_, search_io_;
+  DeviceBuf search_gtab_, search_gd_;  // several ranks: tables of the concatenated list, their all-reduce buffer
   void* host_search_ = nullptr;  // pinned mirror of search_io_ (SearchIO + the `outside` counter)
   bool device_search_ = true;    // env PGN_HOST_SEARCH=1 forces the probe-per-pass search
   // NVLink peer mailboxes for the in-kernel all-reduce of the multi-rank search (threshold_search.cuh)

@@ -160,10 +160,9 @@ k_bucket_count(const double* __restrict__ err, size_t n, BucketPlan plan, Bucket
 }
 
 // one block: exclusive prefix of the bucket counts, cursors
-__global__ void __launch_bounds__(kSearchBlock)
-k_bucket_offsets(BucketPlan plan, BucketTables T)
+__device__ __forceinline__ void
+bucket_offsets_body(const BucketPlan& plan, const BucketTables& T, unsigned long long* s_scan /* [kSearchBlock] */)
 {
-  __shared__ unsigned long long s_scan[kSearchBlock];
   // kMaxBuckets = 2 * kSearchBlock: two buckets per thread
   const uint32_t b0 = 2u * threadIdx.x, b1 = b0 + 1u;
   const unsigned long long c0 = b0 < plan.nb ? T.count[b0] : 0ull;
@@ -187,6 +186,13 @@ k_bucket_offsets(BucketPlan plan, BucketTables T)
   }
   if (threadIdx.x == kSearchBlock - 1)
     T.start[plan.nb] = s_scan[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kSearchBlock)
+k_bucket_offsets(BucketPlan plan, BucketTables T)
+{
+  __shared__ unsigned long long s_scan[kSearchBlock];
+  bucket_offsets_body(plan, T, s_scan);
 }
 
 // Scatter into bucket order.  A block handles chunks of 8192 elements: ranks inside the chunk come
@@ -338,10 +344,9 @@ k_bucket_sums(BucketPlan plan, BucketTables T)
 }
 
 // one block: suffix sums / counts, accumulated from the top bucket down in a fixed order
-__global__ void __launch_bounds__(kSearchBlock)
-k_bucket_suffix(BucketPlan plan, BucketTables T)
+__device__ __forceinline__ void
+bucket_suffix_body(const BucketPlan& plan, const BucketTables& T, double* s_sum /* [kSearchBlock] */)
 {
-  __shared__ double s_sum[kSearchBlock];
   // thread t owns buckets nb-1-2t and nb-2-2t (descending): local sums, then an inclusive scan
   const int nb = static_cast<int>(plan.nb);
   const int k0 = nb - 1 - 2 * static_cast<int>(threadIdx.x), k1 = k0 - 1;
@@ -376,7 +381,78 @@ k_bucket_suffix(BucketPlan plan, BucketTables T)
   }
 }
 
+__global__ void __launch_bounds__(kSearchBlock)
+k_bucket_suffix(BucketPlan plan, BucketTables T)
+{
+  __shared__ double s_sum[kSearchBlock];
+  bucket_suffix_body(plan, T, s_sum);
+}
+
+// ---- several ranks: the tables of the CONCATENATED list ---------------------------------------------------------
+// Counts and integer bucket sums are all-reduced ONCE per search; the suffix tables built from the totals are then
+// bit for bit those a single rank would build over the concatenated list (integer additions commute), every rank
+// holds them, and the bisection needs a peer exchange only for the probes the tables cannot decide (k_search<true>).
+// The totals travel as doubles through the communicator's sum all-reduce: after the carry each piece is an integer
+// below 2^45 (hi) or 2^32 (lo) or 2^24 (count), so sums over <= 16 ranks are exact in any order.
+// g: [nb] counts, [nb] low pieces, [nb] high pieces, [1] values outside the representable range
+__global__ void __launch_bounds__(kSearchBlock)
+k_tables_to_double(BucketPlan plan, BucketTables T, double* __restrict__ g)
+{
+  for (uint32_t b = threadIdx.x; b < plan.nb; b += kSearchBlock) {
+    unsigned long long lo = T.acc_lo[b], hi = T.acc_hi[b];
+    hi += lo >> 32;
+    lo &= 0xffffffffull;
+    g[b] = static_cast<double>(T.count[b]);
+    g[plan.nb + b] = static_cast<double>(lo);
+    g[2 * plan.nb + b] = static_cast<double>(hi);
+  }
+  if (threadIdx.x == 0)
+    g[3 * plan.nb] = static_cast<double>(*T.outside);
+}
+
+// one block: the all-reduced totals back into integer tables, then offsets and suffix tables as for a local list
+__global__ void __launch_bounds__(kSearchBlock)
+k_global_tables(BucketPlan plan, const double* __restrict__ g, BucketTables G)
+{
+  __shared__ unsigned long long s_scan[kSearchBlock];
+  __shared__ double s_sum[kSearchBlock];
+  for (uint32_t b = threadIdx.x; b < plan.nb; b += kSearchBlock) {
+    G.count[b] = static_cast<unsigned long long>(g[b]);
+    G.acc_lo[b] = static_cast<unsigned long long>(g[plan.nb + b]);
+    G.acc_hi[b] = static_cast<unsigned long long>(g[2 * plan.nb + b]);
+  }
+  if (threadIdx.x == 0)
+    *G.outside = static_cast<unsigned long long>(g[3 * plan.nb]);
+  __syncthreads();
+  bucket_offsets_body(plan, G, s_scan);
+  __syncthreads();
+  bucket_suffix_body(plan, G, s_sum);
+}
+
 // ---- probe ----------------------------------------------------------------------------------------
+// elements of bucket tb strictly above t: how many, and the exact integer sum of their mantissas at the bucket's
+// scale (low / high 32-bit pieces); block-collective, results in every thread
+__device__ __forceinline__ void
+scan_bucket_above(double t, uint32_t tb, int eref, const BucketTables& T, unsigned long long (*s_red)[3],
+                  unsigned long long* count, unsigned long long* sum_lo, unsigned long long* sum_hi)
+{
+  const unsigned long long lo_i = T.start[tb], hi_i = T.start[tb + 1];
+  unsigned long long cnt = 0, lo = 0, hi = 0;
+  for (unsigned long long i = lo_i + threadIdx.x; i < hi_i; i += blockDim.x) {
+    const double e = T.sorted[i];
+    if (e > t) {
+      const unsigned long long m = scaled_mantissa(static_cast<unsigned long long>(__double_as_longlong(e)), eref);
+      lo += m & 0xffffffffull;
+      hi += m >> 32;
+      ++cnt;
+    }
+  }
+  block_sum3(cnt, lo, hi, s_red);
+  *count = cnt;
+  *sum_lo = lo;
+  *sum_hi = hi;
+}
+
 // count and sum of the errors strictly above t (block-collective, result in every thread)
 __device__ __forceinline__ void
 probe_above(double t, const BucketPlan& plan, const BucketTables& T, unsigned long long (*s_red)[3],
@@ -399,19 +475,9 @@ probe_above(double t, const BucketPlan& plan, const BucketTables& T, unsigned lo
     *sum = 0.0;
     return;
   }
-  const unsigned long long lo_i = T.start[tb], hi_i = T.start[tb + 1];
   const int eref = bucket_exponent(tb, plan);
-  unsigned long long cnt = 0, lo = 0, hi = 0;
-  for (unsigned long long i = lo_i + threadIdx.x; i < hi_i; i += blockDim.x) {
-    const double e = T.sorted[i];
-    if (e > t) {
-      const unsigned long long m = scaled_mantissa(static_cast<unsigned long long>(__double_as_longlong(e)), eref);
-      lo += m & 0xffffffffull;
-      hi += m >> 32;
-      ++cnt;
-    }
-  }
-  block_sum3(cnt, lo, hi, s_red);
+  unsigned long long cnt, lo, hi;
+  scan_bucket_above(t, tb, eref, T, s_red, &cnt, &lo, &hi);
   *count = T.suffix_count[tb + 1] + cnt;
   *sum = T.suffix_sum[tb + 1] + integer_sum_to_double(lo, hi, eref);
 }
@@ -444,16 +510,27 @@ struct SearchIO {
   unsigned long long num_active;
   int pass_mem, pass_budget;
   int probes;   // -1: a peer did not answer; -2: some rank holds NaN / inf / negative errors
-  int probes_computed;  // probes that were not answered from the memo table
+  int probes_computed;  // probes that were not answered from the memo table (several ranks: nor decided by the global tables)
+  int exchanges;        // peer exchanges of this search (several ranks)
 };
 
 // Heuristic_classifier::classify (heuristic_classifier.cuh:362-451), statement for statement, with
 // every thread of the block running the same scalar control flow on the same values and the probe
 // (apply_threshold + reduction + inner_product, :283-325) answered from the bucket tables.
-// MULTI: the per-probe count and sum are all-reduced over the ranks inside the kernel.
+//
+// MULTI (several ranks, T: this rank's partition, G: the tables of the concatenated list, identical on every rank):
+// a probe at threshold t needs the elements above t -- everything in the buckets above t's own bucket tb (known
+// exactly from G) plus the part of bucket tb above t, which is spread over the ranks.  The search only COMPARES the
+// probe's count and sum with limits, and both comparisons are monotone in them, so the bracket
+//     G.suffix_count[tb+1] <= count <= G.suffix_count[tb],
+//     G.suffix_sum[tb+1]   <= sum   <= G.suffix_sum[tb+1] + G.bucket_sum[tb]      (rounding is monotone)
+// decides most probes without any communication; only a probe whose bracket straddles a limit -- and the one probe
+// whose numbers the search returns -- is computed exactly: every rank scans its part of bucket tb, the integer
+// partial sums (exact in any order) are all-reduced over the NVLink mailboxes, and the result is bit for bit what a
+// single rank obtains on the concatenated list.  Every rank takes the same decisions from the same numbers.
 template <bool MULTI>
 __global__ void __launch_bounds__(kSearchBlock)
-k_search(BucketPlan plan, BucketTables T, SearchIO* io, PeerBox box)
+k_search(BucketPlan plan, BucketTables T, BucketTables G, SearchIO* io, PeerBox box)
 {
   __shared__ unsigned long long s_red[32][3];
   __shared__ int s_ok;
@@ -465,7 +542,7 @@ k_search(BucketPlan plan, BucketTables T, SearchIO* io, PeerBox box)
   for (int i = threadIdx.x; i < kProbeCache; i += blockDim.x)
     c_key[i] = ~0ull;  // a NaN pattern: never cached
   __syncthreads();
-  int computed = 0;
+  int computed = 0, exchanges = 0;
   const SearchIO in = *io;
   const double n_d = in.n_regions;
   double range_lo = in.min_err, range_hi = in.max_err;
@@ -483,7 +560,103 @@ k_search(BucketPlan plan, BucketTables T, SearchIO* io, PeerBox box)
   // not to the value `threshold` ends with.  Keep both.
   double applied = threshold;
   unsigned long long seq = in.seq_base;
-  const double outside_local = static_cast<double>(*T.outside);
+  bool failed = false;
+
+  // MULTI: state of the last probe -- exact numbers (num_active, active_err_sum) or a bracket
+  bool exact = true;
+  unsigned long long cnt_lo = 0, cnt_hi = 0;
+  double sum_lo = 0.0, sum_hi = 0.0;
+  // threshold whose sum produced finished_errorest, and whether that sum was exact
+  double fin_thr = threshold;
+  bool fin_exact = true;
+
+  if (MULTI && *G.outside != 0ull) {  // some rank holds NaN / inf / negative errors: every rank sees it here
+    if (threadIdx.x == 0) {
+      io->probes = -2;
+      io->seq_base = seq;
+    }
+    return;
+  }
+
+  // exact numbers of the probe at t (block-collective; MULTI: one peer exchange unless t is in the memo table)
+  auto probe_exact = [&](double t) {
+    const unsigned long long tbits = static_cast<unsigned long long>(__double_as_longlong(t));
+    const unsigned int slot = static_cast<unsigned int>((tbits ^ (tbits >> 19) ^ (tbits >> 41)) & (kProbeCache - 1));
+    if (c_key[slot] == tbits) {
+      num_active = c_cnt[slot];
+      active_err_sum = c_sum[slot];
+      return;
+    }
+    if (!MULTI) {
+      probe_above(t, plan, T, s_red, &num_active, &active_err_sum);
+    } else {
+      const unsigned long long b_bits = tbits & 0x7fffffffffffffffull;
+      const uint32_t tb = bucket_of(b_bits, plan);
+      if (!(t == t) || (!(t < 0.0) && tb >= plan.nb)) {
+        num_active = 0ull;
+        active_err_sum = 0.0;
+      } else if (t < 0.0) {
+        num_active = G.suffix_count[0];
+        active_err_sum = G.suffix_sum[0];
+      } else {
+        const int eref = bucket_exponent(tb, plan);
+        unsigned long long c, lo, hi;
+        scan_bucket_above(t, tb, eref, T, s_red, &c, &lo, &hi);
+        hi += lo >> 32;
+        lo &= 0xffffffffull;
+        double v[3] = {static_cast<double>(c), static_cast<double>(lo), static_cast<double>(hi)};
+        const bool ok = peer_allreduce_sum<3>(box, ++seq, v, s_mine, s_recv, &s_ok);
+        ++exchanges;
+        if (!ok) {
+          failed = true;
+          return;
+        }
+        num_active = G.suffix_count[tb + 1] + static_cast<unsigned long long>(v[0]);
+        active_err_sum = G.suffix_sum[tb + 1] + integer_sum_to_double(static_cast<unsigned long long>(v[1]),
+                                                                       static_cast<unsigned long long>(v[2]), eref);
+      }
+    }
+    __syncthreads();  // every thread has read the old entry
+    if (threadIdx.x == 0 && t == t) {
+      c_key[slot] = tbits;
+      c_cnt[slot] = num_active;
+      c_sum[slot] = active_err_sum;
+    }
+    __syncthreads();
+    ++computed;
+  };
+  // MULTI: bracket of the probe at t from the global tables; exact when t lies outside every populated bucket
+  auto probe_bracket = [&](double t) {
+    const unsigned long long tbits = static_cast<unsigned long long>(__double_as_longlong(t));
+    const unsigned int slot = static_cast<unsigned int>((tbits ^ (tbits >> 19) ^ (tbits >> 41)) & (kProbeCache - 1));
+    exact = true;
+    if (c_key[slot] == tbits) {
+      num_active = c_cnt[slot];
+      active_err_sum = c_sum[slot];
+      return;
+    }
+    const uint32_t tb = bucket_of(tbits & 0x7fffffffffffffffull, plan);
+    if (!(t == t) || (!(t < 0.0) && tb >= plan.nb)) {
+      num_active = 0ull;
+      active_err_sum = 0.0;
+    } else if (t < 0.0) {
+      num_active = G.suffix_count[0];
+      active_err_sum = G.suffix_sum[0];
+    } else if (G.count[tb] == 0ull) {
+      num_active = G.suffix_count[tb + 1];
+      active_err_sum = G.suffix_sum[tb + 1];  // + integer_sum_to_double(0, 0, .) = + 0.0
+    } else {
+      exact = false;
+      cnt_lo = G.suffix_count[tb + 1];
+      cnt_hi = G.suffix_count[tb];
+      sum_lo = G.suffix_sum[tb + 1];
+      sum_hi = sum_lo + G.bucket_sum[tb];
+    }
+  };
+  auto mem_ok = [&](unsigned long long c) {
+    const double pct = static_cast<double>(static_cast<int>(c)) / static_cast<double>(static_cast<int>(n_d));
+    return pct <= max_active;
+  };
 
   do {
     if (!pass_mem && increases <= 20) {
@@ -493,42 +666,20 @@ k_search(BucketPlan plan, BucketTables T, SearchIO* io, PeerBox box)
         // The reference restarts its bisection from the same threshold every time it relaxes a budget,
         // so most probes of a long search repeat earlier ones: (global) results are memoised by the
         // bit pattern of the threshold.  Every rank holds the same cache, so a hit needs no exchange.
-        const unsigned long long tbits = static_cast<unsigned long long>(__double_as_longlong(threshold));
-        const unsigned int slot =
-          static_cast<unsigned int>((tbits ^ (tbits >> 19) ^ (tbits >> 41)) & (kProbeCache - 1));
         ++probes;
         applied = threshold;
-        if (c_key[slot] == tbits) {
-          num_active = c_cnt[slot];
-          active_err_sum = c_sum[slot];
+        if (MULTI) {
+          probe_bracket(threshold);
+          if (!exact && mem_ok(cnt_lo) != mem_ok(cnt_hi)) {
+            probe_exact(threshold);
+            exact = true;
+          }
         } else {
-          probe_above(threshold, plan, T, s_red, &num_active, &active_err_sum);
-          if (MULTI) {
-            double v[3] = {static_cast<double>(num_active), active_err_sum, outside_local};
-            const bool ok = peer_allreduce_sum<3>(box, ++seq, v, s_mine, s_recv, &s_ok);
-            const double cnt = v[0], sum = v[1], outside = v[2];
-            if (!ok || outside != 0.0) {
-              if (threadIdx.x == 0) {
-                io->probes = ok ? -2 : -1;
-                io->seq_base = seq;
-              }
-              return;
-            }
-            num_active = static_cast<unsigned long long>(cnt);
-            active_err_sum = sum;
-          }
-          __syncthreads();  // every thread has read the old entry
-          if (threadIdx.x == 0 && threshold == threshold) {
-            c_key[slot] = tbits;
-            c_cnt[slot] = num_active;
-            c_sum[slot] = active_err_sum;
-          }
-          __syncthreads();
-          ++computed;
+          probe_exact(threshold);
         }
-        const double pct = static_cast<double>(static_cast<int>(num_active)) /
-                           static_cast<double>(static_cast<int>(n_d));
-        pass_mem = pct <= max_active;
+        if (failed)
+          break;
+        pass_mem = exact ? mem_ok(num_active) : mem_ok(cnt_hi);
         if (!pass_mem) {
           range_lo = threshold;
           threshold += fabs(range_hi - threshold) * .5;
@@ -537,11 +688,33 @@ k_search(BucketPlan plan, BucketTables T, SearchIO* io, PeerBox box)
       }
       increases++;
     }
+    if (failed)
+      break;
     if (pass_mem) {
-      const double extra = in.iter_errorest - active_err_sum - in.finished_errorest;
       const double budget = in.target_error - in.cum_errorest;
-      pass_budget = extra <= max_budget * budget;
-      finished_errorest = extra;
+      if (MULTI && !exact) {
+        // extra is monotone (decreasing) in the sum: the bracket's two ends give its two extremes
+        const bool a = in.iter_errorest - sum_hi - in.finished_errorest <= max_budget * budget;
+        const bool b = in.iter_errorest - sum_lo - in.finished_errorest <= max_budget * budget;
+        if (a != b) {
+          probe_exact(applied);
+          exact = true;
+          if (failed)
+            break;
+        } else {
+          pass_budget = a;
+          finished_errorest = in.iter_errorest - sum_lo - in.finished_errorest;  // placeholder, see fin_exact
+          fin_thr = applied;
+          fin_exact = false;
+        }
+      }
+      if (exact) {
+        const double extra = in.iter_errorest - active_err_sum - in.finished_errorest;
+        pass_budget = extra <= max_budget * budget;
+        finished_errorest = extra;
+        fin_thr = applied;
+        fin_exact = true;
+      }
       if (!pass_budget && decreases <= 20) {
         range_hi = threshold;
         threshold -= fabs(range_lo - threshold) * .5;
@@ -564,6 +737,24 @@ k_search(BucketPlan plan, BucketTables T, SearchIO* io, PeerBox box)
     }
   } while (!pass_mem || !pass_budget);
 
+  if (MULTI && !failed) {
+    // the numbers the search returns are exact ones: those of the last probe, and the sum behind finished_errorest
+    if (!fin_exact) {
+      probe_exact(fin_thr);
+      if (!failed)
+        finished_errorest = in.iter_errorest - active_err_sum - in.finished_errorest;
+    }
+    if (!failed && (!exact || !fin_exact))
+      probe_exact(applied);  // (a memo hit when it is the threshold just computed)
+  }
+  if (failed) {
+    if (threadIdx.x == 0) {
+      io->probes = -1;
+      io->seq_base = seq;
+    }
+    return;
+  }
+
   if (threadIdx.x == 0) {
     io->threshold = threshold;
     io->applied_threshold = applied;
@@ -574,6 +765,7 @@ k_search(BucketPlan plan, BucketTables T, SearchIO* io, PeerBox box)
     io->pass_budget = pass_budget ? 1 : 0;
     io->probes = probes;
     io->probes_computed = computed;
+    io->exchanges = exchanges;
     io->seq_base = seq;
   }
 }

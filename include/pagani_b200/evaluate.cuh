@@ -36,6 +36,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <atomic>
 #include <cstring>
 #include <new>
 #include <type_traits>
@@ -73,9 +74,12 @@ constexpr int kWarpsPerBlock = PGN_EVAL_WARPS;
 #define PGN_EVAL_SEGMENTS 0
 #endif
 
-// 1: a last trip none of whose chain-B points exists (8-D: 17 points) evaluates chain A only
+// 1: a last trip none of whose chain-B points exists (8-D: 17 points) evaluates chain A only.  Off: the extra code
+// path costs registers, and with them 13 of the cosine literals ptxas otherwise keeps in registers across the trip
+// loop of F_1_8D are re-loaded every trip (LDC 17 -> 30 per trip, 176 -> 189 instructions): 314 instead of 289 us on
+// 65 536 regions (ncu, session I), bench 2.45 instead of 2.73e11 evaluations/s.
 #ifndef PGN_EVAL_TAIL_A_ONLY
-#define PGN_EVAL_TAIL_A_ONLY 1
+#define PGN_EVAL_TAIL_A_ONLY 0
 #endif
 #ifndef PGN_EVAL_PREFETCH_BOUNDS
 #define PGN_EVAL_PREFETCH_BOUNDS 1
@@ -1126,17 +1130,23 @@ launch_evaluate(F* functor, const pgn_region_view* v)
   // (the two point-loop variants have the same function type, so `auto kernel` alone would share it)
   auto launch = [&](auto tag, size_t smem) -> int {
     constexpr auto kernel = decltype(tag)::value;
-    static int blocks_per_sm = 0;
+    // the shared-memory attribute is per DEVICE: one cache slot per device ordinal (0: not set up yet); atomics,
+    // because hosts driving different engines may arrive here concurrently (the set-up itself is idempotent)
+    constexpr int kMaxDevices = 64;
+    static std::atomic<int> cache[kMaxDevices];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices)
+      return PGN_ERR_CUDA;
+    int blocks_per_sm = cache[dev].load(std::memory_order_acquire);
     if (blocks_per_sm == 0) {
       if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(smem)) != cudaSuccess)
         return PGN_ERR_CUDA;
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kWarpsPerBlock * 32,
                                                         smem) != cudaSuccess ||
-          blocks_per_sm < 1) {
-        blocks_per_sm = 0;
+          blocks_per_sm < 1)
         return PGN_ERR_CUDA;
-      }
+      cache[dev].store(blocks_per_sm, std::memory_order_release);
     }
     const size_t want = (v->n + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const size_t cap = static_cast<size_t>(v->sm_count > 0 ? v->sm_count : 148) * blocks_per_sm;
