@@ -423,7 +423,9 @@ struct EvalTuning;
 #ifndef PGN_EVAL_NO_GENZ_TUNING  // tools/evalbench sweeps the knob through the primary template instead
 template <int N>
 struct EvalTuning<genz::Oscillatory<N>> {
-  static constexpr int kMinBlocks = 5;  // 84 registers with the call-free point loop: 2.73e11 vs 2.70e11 at 4 (r02_evalbench_f.jsonl)
+  // 4 resident blocks (128 registers): every cosine literal stays in a register across the trip loop (5 of the 17 are
+  // re-loaded per trip at 5 blocks): 2.81e11 vs 2.78e11 evaluations/s (profiles/r02_evalbench_j.jsonl, session G alike)
+  static constexpr int kMinBlocks = 4;
 };
 template <int N>
 struct EvalTuning<genz::ProductPeak<N>> {

@@ -14,6 +14,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 NDIMS = [2, 3, 4, 5, 6, 7, 8, 9, 10]
+# 11..15 (PGN_MAX_NDIM) go into a second file: only the arrays the tests compare (the generator matrix of 15-D is
+# 4.5 MB raw, but it holds 11 distinct values and compresses to a few per cent)
+NDIMS_HI = [11, 12, 13, 14, 15]
 
 
 def read_one(path):
@@ -56,6 +59,16 @@ def main():
             for k, v in read_one(os.path.join(tmp, f"rule_ndim{n}.bin")).items():
                 arrays[f"n{n}_{k}"] = v
     dst = os.path.join(ROOT, "tests", "golden", "rule_tables.npz")
+    np.savez_compressed(dst, **arrays)
+    print("wrote", dst, os.path.getsize(dst), "bytes")
+    arrays = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        subprocess.check_call([tool, tmp] + [str(n) for n in NDIMS_HI])
+        for n in NDIMS_HI:
+            one = read_one(os.path.join(tmp, f"rule_ndim{n}.bin"))
+            for k in ("feval", "weights", "scale", "norm", "set_of_point", "generators"):
+                arrays[f"n{n}_{k}"] = one[k]
+    dst = os.path.join(ROOT, "tests", "golden", "rule_tables_hi.npz")
     np.savez_compressed(dst, **arrays)
     print("wrote", dst, os.path.getsize(dst), "bytes")
 

@@ -137,7 +137,8 @@ def _golden(family, ndim, eps):
     return json.load(open(path))
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
+# PGN_TEST_WORLDS=4,8 restricts the rank counts (a multi-GPU box is charged per GPU-minute)
+@pytest.mark.parametrize("world", [int(w) for w in os.environ.get("PGN_TEST_WORLDS", "2,4,8").split(",")])
 @pytest.mark.parametrize("family,ndim,epsrel", [(1, 8, 1e-4), (4, 8, 1e-9), (5, 10, 1e-3)])
 def test_nccl_ranks_follow_the_reference_golden(tmp_path, world, family, ndim, epsrel):
     """One process per GPU over NCCL + the in-kernel NVLink exchanges (fused statistics, threshold search): every rank

@@ -1,6 +1,6 @@
 """Rule tables of the product (host code behind the C ABI) against the reference's own host code.
 
-Golden: tests/golden/rule_tables.npz, written by tests/golden/make_rule_golden.py from
+Golden: tests/golden/rule_tables.npz (ndim 2..10) and rule_tables_hi.npz (11..15), written by tests/golden/make_rule_golden.py from
 quad::Rule<double>::Init (reference cuda/pagani/quad/GPUquad/Rule.cuh:370-510).  Bit-exact.
 """
 import os
@@ -10,7 +10,9 @@ import pytest
 
 import gpuintegration_b200 as pg
 
-GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "rule_tables.npz"))
+GOLDEN = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "rule_tables.npz")))
+# ndim 11..15 (up to PGN_MAX_NDIM), same generator script, the arrays compared below only
+GOLDEN.update(np.load(os.path.join(os.path.dirname(__file__), "golden", "rule_tables_hi.npz")))
 
 
 def bits(a):
@@ -18,7 +20,7 @@ def bits(a):
     return a.view(np.uint64) if a.dtype == np.float64 else a
 
 
-@pytest.mark.parametrize("ndim", range(2, 11))
+@pytest.mark.parametrize("ndim", range(2, 16))
 def test_tables_bit_exact(ndim):
     t = pg.rule_tables(ndim)
     assert pg.feval(ndim) == int(GOLDEN[f"n{ndim}_feval"])
