@@ -1581,12 +1581,19 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
     if (multi)
       fill_peer_box(&box, 4000000000ll);  // ~2 s of SM clocks: the ranks run this kernel in lock step
     PGN_CUDA(cudaMemcpyAsync(search_io_.ptr, h, sizeof *h, cudaMemcpyHostToDevice, stream_));
+    if (search_attr_device_ != device_) {  // per device: once per engine is enough
+      PGN_CUDA(cudaFuncSetAttribute(k_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(kSearchSmemBytes)));
+      PGN_CUDA(cudaFuncSetAttribute(k_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(kSearchSmemBytes)));
+      search_attr_device_ = device_;
+    }
     if (multi)
-      ++launches_, k_search<true><<<1, kSearchBlock, 0, stream_>>>(plan, tables, global_tables,
-                                                                      search_io_.as<SearchIO>(), box);
+      ++launches_, k_search<true><<<1, kSearchBlock, kSearchSmemBytes, stream_>>>(plan, tables, global_tables,
+                                                                                     search_io_.as<SearchIO>(), box);
     else
-      ++launches_, k_search<false><<<1, kSearchBlock, 0, stream_>>>(plan, tables, tables, search_io_.as<SearchIO>(),
-                                                                       box);
+      ++launches_, k_search<false><<<1, kSearchBlock, kSearchSmemBytes, stream_>>>(plan, tables, tables,
+                                                                                      search_io_.as<SearchIO>(), box);
     PGN_CUDA(cudaGetLastError());
     PGN_CUDA(cudaMemcpyAsync(h, search_io_.ptr, sizeof *h, cudaMemcpyDeviceToHost, stream_));
     PGN_CUDA(cudaMemcpyAsync(h_outside, multi ? global_tables.outside : tables.outside, sizeof *h_outside,
@@ -1609,8 +1616,9 @@ Engine::heuristic_classify(size_t n_global, double iter_est, double iter_err, do
       pass_budget = h->pass_budget != 0;
       out->probes += h->probes;
       if (search_debug)
-        std::fprintf(stderr, "[pgn device search] probes=%d computed=%d peer exchanges=%d\n", h->probes,
-                     h->probes_computed, h->exchanges);
+        std::fprintf(stderr, "[pgn device search] n_local=%zu probes=%d computed=%d peer exchanges=%d cycles: kernel=%lld "
+                             "scans=%lld exchanges=%lld elements scanned=%llu\n", n_, h->probes,
+                     h->probes_computed, h->exchanges, h->cycles_total, h->cycles_scan, h->cycles_exchange, h->scanned);
     } else {
       fast = false;  // NaN / inf / negative errors: keep the reference's flag*err semantics exactly
     }

@@ -147,6 +147,7 @@ private:
   pgn_opts opts_;
   int device_ = 0;
   int sm_count_ = 148;
+  int search_attr_device_ = -1; // device on which k_search's shared-memory attribute was set by this engine
   int pairs_attr_device_ = -1;  // device on which k_classify_pairs' shared-memory attribute was last set by this engine
   int eval_variant_ = 0;  // pgn_region_view::reserved: 0 default, 1 shift/mask, 2 byte-permute
   cudaStream_t stream_ = nullptr;

@@ -35,6 +35,7 @@ constexpr int kMaxBuckets = 2048;
 constexpr int kScatterPerThread = 8;
 constexpr int kScatterChunk = kSearchBlock * kScatterPerThread;
 constexpr int kProbeCache = 1024;  // memo table of probe results (power of two)
+constexpr int kSearchRow = kMaxBuckets + 2;                             // one staged table of k_search (8-byte entries)
 
 struct BucketPlan {
   int shift;     // key = bits >> shift
@@ -438,15 +439,29 @@ scan_bucket_above(double t, uint32_t tb, int eref, const BucketTables& T, unsign
 {
   const unsigned long long lo_i = T.start[tb], hi_i = T.start[tb + 1];
   unsigned long long cnt = 0, lo = 0, hi = 0;
-  for (unsigned long long i = lo_i + threadIdx.x; i < hi_i; i += blockDim.x) {
-    const double e = T.sorted[i];
+  auto take = [&](double e) {
     if (e > t) {
       const unsigned long long m = scaled_mantissa(static_cast<unsigned long long>(__double_as_longlong(e)), eref);
       lo += m & 0xffffffffull;
       hi += m >> 32;
       ++cnt;
     }
+  };
+  // one block reads the whole bucket: kAhead independent loads per thread in flight (the scan is latency bound)
+  constexpr int kAhead = 8;
+  unsigned long long i = lo_i + threadIdx.x;
+  const unsigned long long step = blockDim.x;
+  for (; i + (kAhead - 1) * step < hi_i; i += kAhead * step) {
+    double e[kAhead];
+#pragma unroll
+    for (int k = 0; k < kAhead; ++k)
+      e[k] = __ldg(&T.sorted[i + k * step]);
+#pragma unroll
+    for (int k = 0; k < kAhead; ++k)
+      take(e[k]);
   }
+  for (; i < hi_i; i += step)
+    take(__ldg(&T.sorted[i]));
   block_sum3(cnt, lo, hi, s_red);
   *count = cnt;
   *sum_lo = lo;
@@ -512,6 +527,9 @@ struct SearchIO {
   int probes;   // -1: a peer did not answer; -2: some rank holds NaN / inf / negative errors
   int probes_computed;  // probes that were not answered from the memo table (several ranks: nor decided by the global tables)
   int exchanges;        // peer exchanges of this search (several ranks)
+  // where the kernel's time went (SM clock cycles of thread 0; PGN_SEARCH_DEBUG prints them)
+  long long cycles_total, cycles_scan, cycles_exchange;
+  unsigned long long scanned;  // elements read by the bucket scans of this rank
 };
 
 // Heuristic_classifier::classify (heuristic_classifier.cuh:362-451), statement for statement, with
@@ -528,6 +546,27 @@ struct SearchIO {
 // whose numbers the search returns -- is computed exactly: every rank scans its part of bucket tb, the integer
 // partial sums (exact in any order) are all-reduced over the NVLink mailboxes, and the result is bit for bit what a
 // single rank obtains on the concatenated list.  Every rank takes the same decisions from the same numbers.
+// Execution: the bisection is SCALAR control flow (a few hundred probes, most of them answered from the memo table
+// or the brackets), so ONE warp runs it; the other 31 warps of the block wait at a barrier and join only for the
+// block-wide part of an exact probe -- the scan of a bucket and, with several ranks, the peer exchange.  (With all 32
+// warps executing the control flow redundantly a memo-table probe cost 0.5 us of issue slots, 130 us per search.)
+// The brackets are used on one rank too: there they save the scans.
+//
+// Tried and dropped (session L, profiles/r02_search_kernel_sessionL.txt): sub-bin tables of the bucket a bisection
+// converges in (64 bins by the next 6 bits, built by one pass, all-reduced through a wide channel).  One level leaves
+// the tail of every 20-step bisection undecided (its interval ends far narrower than a bin); refining recursively
+// decides everything but needs as many passes as it saves scans, each dearer than a scan (2.3 us).
+constexpr size_t kSearchCacheBytes = kProbeCache * (2 * sizeof(unsigned long long) + sizeof(double));
+constexpr size_t kSearchSmemBytes = sizeof(double) * 5 * kSearchRow + kSearchCacheBytes;  // dynamic shared memory
+
+struct ScanCommand {
+  double t;
+  uint32_t tb;
+  int eref;
+  int leave;
+  unsigned long long seq;
+};
+
 template <bool MULTI>
 __global__ void __launch_bounds__(kSearchBlock)
 k_search(BucketPlan plan, BucketTables T, BucketTables G, SearchIO* io, PeerBox box)
@@ -536,13 +575,70 @@ k_search(BucketPlan plan, BucketTables T, BucketTables G, SearchIO* io, PeerBox 
   __shared__ int s_ok;
   __shared__ double s_mine[3];
   __shared__ uint32_t s_recv[kMaxPeers * 2 * 3];
-  __shared__ unsigned long long c_key[kProbeCache];
-  __shared__ unsigned long long c_cnt[kProbeCache];
-  __shared__ double c_sum[kProbeCache];
+  __shared__ ScanCommand s_cmd;
+  // dynamic: the tables a probe consults, staged once, and the memo table
+  extern __shared__ __align__(16) unsigned char search_smem[];
+  unsigned long long* s_start = reinterpret_cast<unsigned long long*>(search_smem);  // this rank's bucket bounds
+  unsigned long long* s_sufc = s_start + kSearchRow;                                 // suffix counts (MULTI: global)
+  double* s_sufs = reinterpret_cast<double*>(s_sufc + kSearchRow);                   // suffix sums   (MULTI: global)
+  double* s_bsum = s_sufs + kSearchRow;                                              // bucket sums   (MULTI: global)
+  unsigned long long* s_cnt = reinterpret_cast<unsigned long long*>(s_bsum + kSearchRow);  // counts  (MULTI: global)
+  unsigned long long* c_key = s_cnt + kSearchRow;
+  unsigned long long* c_cnt = c_key + kProbeCache;
+  double* c_sum = reinterpret_cast<double*>(c_cnt + kProbeCache);
+  for (uint32_t b = threadIdx.x; b <= plan.nb; b += blockDim.x) {
+    s_start[b] = T.start[b];
+    s_sufc[b] = G.suffix_count[b];
+    s_sufs[b] = G.suffix_sum[b];
+    if (b < plan.nb) {
+      s_bsum[b] = G.bucket_sum[b];
+      s_cnt[b] = G.count[b];
+    }
+  }
+  const unsigned long long outside_global = *G.outside;
+  T.start = s_start;
   for (int i = threadIdx.x; i < kProbeCache; i += blockDim.x)
     c_key[i] = ~0ull;  // a NaN pattern: never cached
   __syncthreads();
+
+  long long c_xchg = 0;
+  // block-wide (every thread, after the command barrier): elements of bucket cmd.tb above cmd.t -- count and integer
+  // mantissa sum, over all ranks when MULTI; results in every thread
+  auto collective_scan = [&](const ScanCommand cmd, unsigned long long* c, unsigned long long* lo,
+                             unsigned long long* hi) -> bool {
+    scan_bucket_above(cmd.t, cmd.tb, cmd.eref, T, s_red, c, lo, hi);
+    *hi += *lo >> 32;
+    *lo &= 0xffffffffull;
+    if (!MULTI)
+      return true;
+    const long long c0 = clock64();
+    double v[3] = {static_cast<double>(*c), static_cast<double>(*lo), static_cast<double>(*hi)};
+    const bool ok = peer_allreduce_sum<3>(box, cmd.seq, v, s_mine, s_recv, &s_ok);
+    *c = static_cast<unsigned long long>(v[0]);
+    *lo = static_cast<unsigned long long>(v[1]);
+    *hi = static_cast<unsigned long long>(v[2]);
+    c_xchg += clock64() - c0;
+    return ok;
+  };
+
+  if (threadIdx.x >= 32) {
+    // worker warps: wait for a command, join the block-wide operation, until told to leave
+    for (;;) {
+      __syncthreads();
+      const ScanCommand cmd = s_cmd;
+      if (cmd.leave)
+        return;
+      unsigned long long c, lo, hi;
+      collective_scan(cmd, &c, &lo, &hi);
+    }
+  }
+
+  // ---- warp 0: the search ----------------------------------------------------------------------------------------
+  const int lane = threadIdx.x;
   int computed = 0, exchanges = 0;
+  const long long c_begin = clock64();
+  long long c_scan = 0;
+  unsigned long long scanned = 0;
   const SearchIO in = *io;
   const double n_d = in.n_regions;
   double range_lo = in.min_err, range_hi = in.max_err;
@@ -562,7 +658,7 @@ k_search(BucketPlan plan, BucketTables T, BucketTables G, SearchIO* io, PeerBox 
   unsigned long long seq = in.seq_base;
   bool failed = false;
 
-  // MULTI: state of the last probe -- exact numbers (num_active, active_err_sum) or a bracket
+  // state of the last probe: exact numbers (num_active, active_err_sum) or a bracket
   bool exact = true;
   unsigned long long cnt_lo = 0, cnt_hi = 0;
   double sum_lo = 0.0, sum_hi = 0.0;
@@ -570,65 +666,78 @@ k_search(BucketPlan plan, BucketTables T, BucketTables G, SearchIO* io, PeerBox 
   double fin_thr = threshold;
   bool fin_exact = true;
 
-  if (MULTI && *G.outside != 0ull) {  // some rank holds NaN / inf / negative errors: every rank sees it here
-    if (threadIdx.x == 0) {
+  auto post = [&](bool leave, double t, uint32_t tb, int eref, bool exchange) {
+    if (lane == 0) {
+      s_cmd.t = t;
+      s_cmd.tb = tb;
+      s_cmd.eref = eref;
+      s_cmd.leave = leave ? 1 : 0;
+      s_cmd.seq = exchange ? ++seq : seq;
+    }
+    seq = __shfl_sync(0xffffffffu, seq, 0);
+    __syncthreads();  // the command barrier: the worker warps pick the command up
+  };
+
+  if (MULTI && outside_global != 0ull) {  // some rank holds NaN / inf / negative errors: every rank sees it here
+    if (lane == 0) {
       io->probes = -2;
       io->seq_base = seq;
     }
+    post(true, 0.0, 0u, 0, false);
     return;
   }
 
-  // exact numbers of the probe at t (block-collective; MULTI: one peer exchange unless t is in the memo table)
+  auto cache_slot = [&](unsigned long long tbits) {
+    return static_cast<unsigned int>((tbits ^ (tbits >> 19) ^ (tbits >> 41)) & (kProbeCache - 1));
+  };
+  // exact numbers of the probe at t: from the memo table, trivially, or by a block-wide scan (MULTI: + one exchange)
   auto probe_exact = [&](double t) {
     const unsigned long long tbits = static_cast<unsigned long long>(__double_as_longlong(t));
-    const unsigned int slot = static_cast<unsigned int>((tbits ^ (tbits >> 19) ^ (tbits >> 41)) & (kProbeCache - 1));
+    const unsigned int slot = cache_slot(tbits);
     if (c_key[slot] == tbits) {
       num_active = c_cnt[slot];
       active_err_sum = c_sum[slot];
       return;
     }
-    if (!MULTI) {
-      probe_above(t, plan, T, s_red, &num_active, &active_err_sum);
+    const uint32_t tb = bucket_of(tbits & 0x7fffffffffffffffull, plan);
+    if (!(t == t) || (!(t < 0.0) && tb >= plan.nb)) {  // e > NaN is false for every e; t above the largest error
+      num_active = 0ull;
+      active_err_sum = 0.0;
+    } else if (t < 0.0) {
+      num_active = s_sufc[0];
+      active_err_sum = s_sufs[0];
     } else {
-      const unsigned long long b_bits = tbits & 0x7fffffffffffffffull;
-      const uint32_t tb = bucket_of(b_bits, plan);
-      if (!(t == t) || (!(t < 0.0) && tb >= plan.nb)) {
-        num_active = 0ull;
-        active_err_sum = 0.0;
-      } else if (t < 0.0) {
-        num_active = G.suffix_count[0];
-        active_err_sum = G.suffix_sum[0];
-      } else {
-        const int eref = bucket_exponent(tb, plan);
-        unsigned long long c, lo, hi;
-        scan_bucket_above(t, tb, eref, T, s_red, &c, &lo, &hi);
-        hi += lo >> 32;
-        lo &= 0xffffffffull;
-        double v[3] = {static_cast<double>(c), static_cast<double>(lo), static_cast<double>(hi)};
-        const bool ok = peer_allreduce_sum<3>(box, ++seq, v, s_mine, s_recv, &s_ok);
+      const int eref = bucket_exponent(tb, plan);
+      const long long c0 = clock64();
+      post(false, t, tb, eref, MULTI);
+      const ScanCommand cmd = s_cmd;
+      unsigned long long c, lo, hi;
+      const bool ok = collective_scan(cmd, &c, &lo, &hi);
+      c_scan += clock64() - c0;
+      scanned += s_start[tb + 1] - s_start[tb];
+      if (MULTI)
         ++exchanges;
-        if (!ok) {
-          failed = true;
-          return;
-        }
-        num_active = G.suffix_count[tb + 1] + static_cast<unsigned long long>(v[0]);
-        active_err_sum = G.suffix_sum[tb + 1] + integer_sum_to_double(static_cast<unsigned long long>(v[1]),
-                                                                       static_cast<unsigned long long>(v[2]), eref);
+      if (!ok) {
+        failed = true;
+        return;
       }
+      num_active = s_sufc[tb + 1] + c;
+      active_err_sum = s_sufs[tb + 1] + integer_sum_to_double(lo, hi, eref);
     }
-    __syncthreads();  // every thread has read the old entry
-    if (threadIdx.x == 0 && t == t) {
+    __syncwarp();  // every lane has read the old entry (only this warp uses the memo table)
+    if (lane == 0 && t == t) {
       c_key[slot] = tbits;
       c_cnt[slot] = num_active;
       c_sum[slot] = active_err_sum;
     }
-    __syncthreads();
+    __syncwarp();
     ++computed;
   };
-  // MULTI: bracket of the probe at t from the global tables; exact when t lies outside every populated bucket
+  // bracket of the probe at t from the bucket tables; exact when the memo table has it or when t lies outside every
+  // populated bucket
   auto probe_bracket = [&](double t) {
     const unsigned long long tbits = static_cast<unsigned long long>(__double_as_longlong(t));
-    const unsigned int slot = static_cast<unsigned int>((tbits ^ (tbits >> 19) ^ (tbits >> 41)) & (kProbeCache - 1));
+    const unsigned int slot = cache_slot(tbits);
     exact = true;
     if (c_key[slot] == tbits) {
       num_active = c_cnt[slot];
@@ -640,22 +749,52 @@ k_search(BucketPlan plan, BucketTables T, BucketTables G, SearchIO* io, PeerBox 
       num_active = 0ull;
       active_err_sum = 0.0;
     } else if (t < 0.0) {
-      num_active = G.suffix_count[0];
-      active_err_sum = G.suffix_sum[0];
-    } else if (G.count[tb] == 0ull) {
-      num_active = G.suffix_count[tb + 1];
-      active_err_sum = G.suffix_sum[tb + 1];  // + integer_sum_to_double(0, 0, .) = + 0.0
+      num_active = s_sufc[0];
+      active_err_sum = s_sufs[0];
+    } else if (s_cnt[tb] == 0ull) {
+      num_active = s_sufc[tb + 1];
+      active_err_sum = s_sufs[tb + 1];  // + integer_sum_to_double(0, 0, .) = + 0.0
     } else {
       exact = false;
-      cnt_lo = G.suffix_count[tb + 1];
-      cnt_hi = G.suffix_count[tb];
-      sum_lo = G.suffix_sum[tb + 1];
-      sum_hi = sum_lo + G.bucket_sum[tb];
+      cnt_lo = s_sufc[tb + 1];
+      cnt_hi = s_sufc[tb];
+      sum_lo = s_sufs[tb + 1];
+      sum_hi = sum_lo + s_bsum[tb];
     }
   };
-  auto mem_ok = [&](unsigned long long c) {
+  // pct <= max_active with the reference's int casts and division (heuristic_classifier.cuh:394-396).  Monotone in
+  // the count, so the largest passing count is found once per value of max_active (31 divisions) and a probe then
+  // costs an integer comparison instead of a correctly rounded division on the scalar critical path.
+  const bool small_n = n_d < 2147483648.0;
+  auto mem_ok_div = [&](unsigned long long c) {
     const double pct = static_cast<double>(static_cast<int>(c)) / static_cast<double>(static_cast<int>(n_d));
     return pct <= max_active;
+  };
+  double limit_for = -1.0;  // max_active the cached limit belongs to
+  long long limit = -1;     // largest count that passes (-1: none)
+  auto mem_ok = [&](unsigned long long c) {
+    if (!small_n || c > static_cast<unsigned long long>(static_cast<long long>(n_d)))
+      return mem_ok_div(c);
+    if (limit_for != max_active) {
+      long long a = -1, b = static_cast<long long>(n_d);  // a passes (or is -1), b fails (or is n and untested)
+      if (mem_ok_div(static_cast<unsigned long long>(b))) {
+        a = b;
+      } else {
+        while (b - a > 1) {
+          const long long mid = a + (b - a) / 2;
+          if (mem_ok_div(static_cast<unsigned long long>(mid)))
+            a = mid;
+          else
+            b = mid;
+        }
+      }
+      limit = a;
+      limit_for = max_active;
+    }
+    return static_cast<long long>(c) <= limit;
+  };
+  auto budget_ok = [&](double sum, double budget) {
+    return in.iter_errorest - sum - in.finished_errorest <= max_budget * budget;
   };
 
   do {
@@ -665,17 +804,13 @@ k_search(BucketPlan plan, BucketTables T, BucketTables G, SearchIO* io, PeerBox 
       while (!pass_mem && attempts < 20) {
         // The reference restarts its bisection from the same threshold every time it relaxes a budget,
         // so most probes of a long search repeat earlier ones: (global) results are memoised by the
-        // bit pattern of the threshold.  Every rank holds the same cache, so a hit needs no exchange.
+        // bit pattern of the threshold.  Every rank holds the same table, so a hit needs no exchange.
         ++probes;
         applied = threshold;
-        if (MULTI) {
-          probe_bracket(threshold);
-          if (!exact && mem_ok(cnt_lo) != mem_ok(cnt_hi)) {
-            probe_exact(threshold);
-            exact = true;
-          }
-        } else {
+        probe_bracket(threshold);
+        if (!exact && mem_ok(cnt_lo) != mem_ok(cnt_hi)) {
           probe_exact(threshold);
+          exact = true;
         }
         if (failed)
           break;
@@ -692,10 +827,9 @@ k_search(BucketPlan plan, BucketTables T, BucketTables G, SearchIO* io, PeerBox 
       break;
     if (pass_mem) {
       const double budget = in.target_error - in.cum_errorest;
-      if (MULTI && !exact) {
+      if (!exact) {
         // extra is monotone (decreasing) in the sum: the bracket's two ends give its two extremes
-        const bool a = in.iter_errorest - sum_hi - in.finished_errorest <= max_budget * budget;
-        const bool b = in.iter_errorest - sum_lo - in.finished_errorest <= max_budget * budget;
+        const bool a = budget_ok(sum_hi, budget), b = budget_ok(sum_lo, budget);
         if (a != b) {
           probe_exact(applied);
           exact = true;
@@ -737,7 +871,7 @@ k_search(BucketPlan plan, BucketTables T, BucketTables G, SearchIO* io, PeerBox 
     }
   } while (!pass_mem || !pass_budget);
 
-  if (MULTI && !failed) {
+  if (!failed) {
     // the numbers the search returns are exact ones: those of the last probe, and the sum behind finished_errorest
     if (!fin_exact) {
       probe_exact(fin_thr);
@@ -747,25 +881,26 @@ k_search(BucketPlan plan, BucketTables T, BucketTables G, SearchIO* io, PeerBox 
     if (!failed && (!exact || !fin_exact))
       probe_exact(applied);  // (a memo hit when it is the threshold just computed)
   }
-  if (failed) {
-    if (threadIdx.x == 0) {
+  post(true, 0.0, 0u, 0, false);
+  if (lane == 0) {
+    if (failed) {
       io->probes = -1;
-      io->seq_base = seq;
+    } else {
+      io->threshold = threshold;
+      io->applied_threshold = applied;
+      io->active_err_sum = active_err_sum;
+      io->extra_finished_errorest = finished_errorest;
+      io->num_active = num_active;
+      io->pass_mem = pass_mem ? 1 : 0;
+      io->pass_budget = pass_budget ? 1 : 0;
+      io->probes = probes;
+      io->probes_computed = computed;
+      io->exchanges = exchanges;
+      io->cycles_total = clock64() - c_begin;
+      io->cycles_scan = c_scan;
+      io->cycles_exchange = c_xchg;
+      io->scanned = scanned;
     }
-    return;
-  }
-
-  if (threadIdx.x == 0) {
-    io->threshold = threshold;
-    io->applied_threshold = applied;
-    io->active_err_sum = active_err_sum;
-    io->extra_finished_errorest = finished_errorest;
-    io->num_active = num_active;
-    io->pass_mem = pass_mem ? 1 : 0;
-    io->pass_budget = pass_budget ? 1 : 0;
-    io->probes = probes;
-    io->probes_computed = computed;
-    io->exchanges = exchanges;
     io->seq_base = seq;
   }
 }
