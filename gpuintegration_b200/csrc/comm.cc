@@ -133,20 +133,17 @@ public:
   {
     if (api->GroupStart() != ncclSuccess)
       return PGN_ERR_NCCL;
-    for (size_t k = 0; k < plan.size(); ++k) {
+    bool ok = true;  // a failed call must not leave the group open: GroupEnd runs in every case
+    for (size_t k = 0; k < plan.size() && ok; ++k) {
       const Transfer& t = plan[k];
       if (t.src == t.dst)
         continue;
-      if (t.src == rank &&
-          api->Send(send_base + send_off[k], t.count * dpr, ncclDouble, t.dst, comm, stream) !=
-            ncclSuccess)
-        return PGN_ERR_NCCL;
-      if (t.dst == rank &&
-          api->Recv(recv_base + recv_off[k], t.count * dpr, ncclDouble, t.src, comm, stream) !=
-            ncclSuccess)
-        return PGN_ERR_NCCL;
+      if (t.src == rank)
+        ok = api->Send(send_base + send_off[k], t.count * dpr, ncclDouble, t.dst, comm, stream) == ncclSuccess;
+      if (ok && t.dst == rank)
+        ok = api->Recv(recv_base + recv_off[k], t.count * dpr, ncclDouble, t.src, comm, stream) == ncclSuccess;
     }
-    return api->GroupEnd() == ncclSuccess ? PGN_OK : PGN_ERR_NCCL;
+    return api->GroupEnd() == ncclSuccess && ok ? PGN_OK : PGN_ERR_NCCL;
   }
   const char* name() const override { return "nccl"; }
 };

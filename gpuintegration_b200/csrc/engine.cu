@@ -230,7 +230,8 @@ Engine::~Engine()
                       &length_[0], &length_[1], &est_,        &err_raw_,    &err_ref_,    &axis_,
                       &active_,    &par_est_[0], &par_est_[1], &par_err_[0], &par_err_[1], &par_axis_,
                       &partials_,  &tile_count_, &tile_offset_, &done_,      &stats_dev_,  &stats_glob_,
-                      &digest_dev_, &pack_send_, &pack_recv_, &sorted_err_, &search_tab_, &search_io_, &mailbox_};
+                      &digest_dev_, &pack_send_, &pack_recv_, &sorted_err_, &search_tab_, &search_io_, &mailbox_,
+                      &search_gtab_, &search_gd_, &par_axis_next_};
   for (DeviceBuf* b : all)
     b->release();
   if (host_local_)
@@ -1299,7 +1300,7 @@ Engine::rebalance_parents(size_t* m_local)
   PGN_TRY(par_err_[pn].reserve(sizeof(double) * std::max<size_t>(m_new, 1)));
   // the split axes are unpacked in place: every byte of par_axis_ was packed already
   PGN_CUDA(cudaStreamSynchronize(stream_));
-  DeviceBuf new_axis;
+  DeviceBuf& new_axis = par_axis_next_;  // grow-only twin of par_axis_: no allocation per rebalance, nothing to leak
   PGN_TRY(new_axis.reserve(sizeof(int32_t) * std::max<size_t>(m_new, 1)));
   for (size_t k = 0; k < plan.size(); ++k) {
     const Transfer& t = plan[k];
@@ -1312,8 +1313,7 @@ Engine::rebalance_parents(size_t* m_local)
   }
   PGN_CUDA(cudaGetLastError());
   PGN_CUDA(cudaStreamSynchronize(stream_));
-  par_axis_.release();
-  par_axis_ = new_axis;
+  std::swap(par_axis_, par_axis_next_);
   cur_ = nxt;
   par_cur_ = pn;
   *m_local = m_new;
@@ -2013,29 +2013,30 @@ Engine::setup_peer_mailboxes()
 {
   release_peer_mailboxes();
   const int w = comm_->nranks, me = comm_->rank;
-  PGN_TRY(mailbox_.reserve(kMailboxBytes));
-  PGN_CUDA(cudaMemset(mailbox_.ptr, 0, kMailboxBytes));
+  // A rank that fails locally (allocation, IPC export) must still take part in both all-reduces below -- its peers
+  // would otherwise wait in them for ever -- and simply votes against the in-kernel path.
+  bool local_ok = mailbox_.reserve(kMailboxBytes) == PGN_OK;
   cudaIpcMemHandle_t mine;
-  PGN_CUDA(cudaIpcGetMemHandle(&mine, mailbox_.ptr));
+  std::memset(&mine, 0, sizeof mine);
+  if (local_ok && (cudaMemset(mailbox_.ptr, 0, kMailboxBytes) != cudaSuccess ||
+                   cudaIpcGetMemHandle(&mine, mailbox_.ptr) != cudaSuccess)) {
+    cudaGetLastError();
+    local_ok = false;
+  }
   constexpr int kH = static_cast<int>(sizeof(cudaIpcMemHandle_t));
   std::vector<double> table(static_cast<size_t>(w) * kH, 0.0);
   const unsigned char* bytes = reinterpret_cast<const unsigned char*>(&mine);
   for (int i = 0; i < kH; ++i)
     table[static_cast<size_t>(me) * kH + i] = static_cast<double>(bytes[i]);
-  DeviceBuf xchg;
-  PGN_TRY(xchg.reserve(sizeof(double) * table.size()));
-  PGN_CUDA(cudaMemcpyAsync(xchg.ptr, table.data(), sizeof(double) * table.size(), cudaMemcpyHostToDevice,
-                           stream_));
-  int rc = comm_->allreduce(xchg.as<double>(), static_cast<int>(table.size()), kOpSum, stream_);
-  if (rc == PGN_OK &&
-      (cudaMemcpyAsync(table.data(), xchg.ptr, sizeof(double) * table.size(), cudaMemcpyDeviceToHost,
-                       stream_) != cudaSuccess ||
-       cudaStreamSynchronize(stream_) != cudaSuccess))
-    rc = PGN_ERR_CUDA;
-  xchg.release();
-  PGN_TRY(rc);
+  // scratch: the (grow-only) rebalance staging buffer, idle here
+  PGN_TRY(pack_send_.reserve(sizeof(double) * table.size()));
+  double* xchg = pack_send_.as<double>();
+  PGN_CUDA(cudaMemcpyAsync(xchg, table.data(), sizeof(double) * table.size(), cudaMemcpyHostToDevice, stream_));
+  PGN_TRY(comm_->allreduce(xchg, static_cast<int>(table.size()), kOpSum, stream_));
+  PGN_CUDA(cudaMemcpyAsync(table.data(), xchg, sizeof(double) * table.size(), cudaMemcpyDeviceToHost, stream_));
+  PGN_CUDA(cudaStreamSynchronize(stream_));
   peer_mapped_.assign(w, nullptr);
-  bool ok = true;
+  bool ok = local_ok;
   for (int q = 0; q < w && ok; ++q) {
     if (q == me)
       continue;
@@ -2053,16 +2054,10 @@ Engine::setup_peer_mailboxes()
   }
   // every rank must agree on whether the in-kernel path is usable
   double agree = ok ? 0.0 : 1.0;
-  DeviceBuf flag;
-  PGN_TRY(flag.reserve(sizeof(double)));
-  PGN_CUDA(cudaMemcpyAsync(flag.ptr, &agree, sizeof agree, cudaMemcpyHostToDevice, stream_));
-  rc = comm_->allreduce(flag.as<double>(), 1, kOpSum, stream_);
-  if (rc == PGN_OK && (cudaMemcpyAsync(&agree, flag.ptr, sizeof agree, cudaMemcpyDeviceToHost, stream_) !=
-                         cudaSuccess ||
-                       cudaStreamSynchronize(stream_) != cudaSuccess))
-    rc = PGN_ERR_CUDA;
-  flag.release();
-  PGN_TRY(rc);
+  PGN_CUDA(cudaMemcpyAsync(xchg, &agree, sizeof agree, cudaMemcpyHostToDevice, stream_));
+  PGN_TRY(comm_->allreduce(xchg, 1, kOpSum, stream_));
+  PGN_CUDA(cudaMemcpyAsync(&agree, xchg, sizeof agree, cudaMemcpyDeviceToHost, stream_));
+  PGN_CUDA(cudaStreamSynchronize(stream_));
   peer_ready_ = agree == 0.0;
   peer_seq_ = 0;
   if (!peer_ready_)

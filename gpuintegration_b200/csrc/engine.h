@@ -169,7 +169,7 @@ private:
   bool evaluated_ = false, classified_ = false;
   const double* err_cur_ = nullptr;  // refined errors when parents exist, raw otherwise
   // parents (previous iteration's surviving estimates), double buffered
-  DeviceBuf par_est_[2], par_err_[2], par_axis_;
+  DeviceBuf par_est_[2], par_err_[2], par_axis_, par_axis_next_;
   int par_cur_ = 0;
   size_t parents_n_ = 0;  // 0: no parents (iteration 0)
   bool filtered_pending_ = false;  // filter() done, split() not yet: cur list = compacted parents
