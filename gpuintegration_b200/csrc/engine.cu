@@ -848,13 +848,11 @@ Engine::classify(double epsrel, int relerr, pgn_iter_stats* out)
   if (out) {
     std::memset(out, 0, sizeof *out);
     out->nregions = n_;
-    size_t ng = 0;
     out->iter_estimate = host_global_[kSumEst];
     out->iter_errorest = host_global_[kSumErr];
     out->finished_estimate = host_global_[kSumEst] - host_global_[kSumActEst];
     out->finished_errorest = host_global_[kSumErr] - host_global_[kSumActErr];
     out->nactive = static_cast<uint64_t>(host_global_[kNumActive]);
-    (void)ng;
   }
   return PGN_OK;
 }
