@@ -4,8 +4,7 @@ constructed list that takes the "exhausted right after a successful probe" path 
 the last probe, heuristic_classifier.cuh:404-437 / Workspace.cuh:104-106).  The CPU oracle runs the same two
 cases in tests/test_oracle_golden.py; here engine and oracle must agree, device-side and host-side search.
 
-The entry point was written after the round's GPU time was used up: its first run on a GPU is the driver's
-round-end run, hence the non-strict xfail (a pass shows up as XPASS; remove the marker then)."""
+(Passing on the GPU since the driver's round-1 run; part of every round-2 session's suite.)"""
 import os
 
 import numpy as np
@@ -13,8 +12,7 @@ import pytest
 
 import oracle_cpu
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="pgn_heuristic_classify: first GPU run pending (added without GPU time left)")]
+pytestmark = pytest.mark.gpu
 
 
 def run_case(pg, errors, last_estimate, epsrel, total_finished, host_search):
