@@ -675,8 +675,15 @@ Engine::make_scratch(bool allow_fused)
   stats_published_ = host_pub_dev_ != nullptr;
   stats_fused_ = false;
   if (allow_fused && comm_ && comm_->nranks > 1 && peer_ready_) {
-    // a peer may still be inside a long evaluation kernel: allow about a minute of skew
-    fill_peer_box(&ts.box, 120000000000ll);
+    // A peer may still be inside a long evaluation kernel (seconds on a list of 10^8 regions), so the wait is generous:
+    // 6e10 SM clocks, about half a minute, after which the kernel gives up, the statistics come back as NaN and the
+    // call fails with PGN_ERR_NCCL instead of hanging on a lost peer.  PGN_PEER_SPIN_TICKS overrides it.
+    static const long long spin_ticks = [] {
+      const char* e = std::getenv("PGN_PEER_SPIN_TICKS");
+      const long long v = e ? std::atoll(e) : 0;
+      return v > 0 ? v : 60000000000ll;
+    }();
+    fill_peer_box(&ts.box, spin_ticks);
     ts.seq = ++stats_seq_;
     stats_fused_ = true;
   }

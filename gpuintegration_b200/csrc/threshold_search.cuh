@@ -10,8 +10,12 @@
 // is monotone in its value, so a bucket is a range of leading bits), and a probe becomes
 //     count(err > t) = count of all higher buckets  +  a scan of the one bucket that contains t
 // which a single thread block answers in a few microseconds.  The whole bisection (the reference's exact
-// threshold sequence and decisions) then runs inside ONE kernel, k_search, with no host round trip;
-// multi-rank runs use the same per-probe query (k_query) and all-reduce its two numbers.
+// threshold sequence and decisions) then runs inside ONE kernel, k_search, with no host round trip.
+// Several ranks: the bucket counts and integer sums are all-reduced once per search (k_tables_to_double ->
+// communicator -> k_global_tables), so every rank holds the tables of the CONCATENATED list and walks through the
+// same bisection; only probes those tables cannot decide are scanned and exchanged over the NVLink mailboxes
+// (peer.cuh), with results bit for bit those of a single rank.  Without peer access the host drives the search
+// with one k_query + all-reduce per probe.
 //
 // Sums are order independent by construction: inside a bucket every element has the same exponent, so
 // the mantissas are added as integers (exactly), and bucket totals are combined in a fixed order.
