@@ -84,6 +84,16 @@ constexpr int kWarpsPerBlock = PGN_EVAL_WARPS;
 #ifndef PGN_EVAL_PREFETCH_BOUNDS
 #define PGN_EVAL_PREFETCH_BOUNDS 1
 #endif
+// 1: the PER-LANE rule weights (first and last trip, trips that straddle a generator-set boundary: 6 of 17 at 8-D)
+// come from a shared-memory copy of the weight table instead of the constant bank: a constant-bank read whose
+// address differs between the lanes is replayed once per distinct address, a shared-memory read of two distinct rows
+// is one wavefront.  +1.1 % on F_1_8D (2.815 -> 2.845e11 evaluations/s, profiles/r02_evalbench_s.jsonl), same bits;
+// within +-0.3 % for the other families except the 10-D discontinuous one (-2.6 %: its gather already loads the
+// shared-memory pipe).  Off by default; a functor opts in through EvalTuning<F>::kLaneWeightsSmem.
+// (Loading the code words of trip t+1 during trip t, also tried there, is 0.7 % slower.)
+#ifndef PGN_EVAL_LANE_WEIGHTS_SMEM
+#define PGN_EVAL_LANE_WEIGHTS_SMEM 0
+#endif
 
 // Launch-bound tuning knob of the evaluation kernel: resident 128-thread blocks per SM the register
 // allocation must allow (4 -> up to 128 registers per thread, 7 -> 72, 8 -> 64).  Cheap integrands
@@ -93,6 +103,7 @@ template <typename F>
 struct EvalTuning {
   static constexpr int kMinBlocks = PGN_EVAL_MIN_BLOCKS;
   static constexpr bool kSegments = PGN_EVAL_SEGMENTS != 0;
+  static constexpr bool kLaneWeightsSmem = PGN_EVAL_LANE_WEIGHTS_SMEM != 0;
 };
 // kSegments of a specialisation that does not declare it: the default
 template <typename F, class = void>
@@ -100,6 +111,12 @@ struct eval_segments : std::integral_constant<bool, PGN_EVAL_SEGMENTS != 0> {};
 template <typename F>
 struct eval_segments<F, std::void_t<decltype(EvalTuning<F>::kSegments)>>
   : std::integral_constant<bool, EvalTuning<F>::kSegments> {};
+// likewise kLaneWeightsSmem
+template <typename F, class = void>
+struct eval_lane_weights_smem : std::integral_constant<bool, PGN_EVAL_LANE_WEIGHTS_SMEM != 0> {};
+template <typename F>
+struct eval_lane_weights_smem<F, std::void_t<decltype(EvalTuning<F>::kLaneWeightsSmem)>>
+  : std::integral_constant<bool, EvalTuning<F>::kLaneWeightsSmem> {};
 constexpr int kWeightRow = 6;  // 5 rule weights padded to 48 B so a row is three 16-byte loads
 
 // values of pgn_region_view::reserved
@@ -561,7 +578,7 @@ struct BpLayout {
   static constexpr int kCodeWords = NDIM <= 8 ? 2 : 4;  // 32-bit words per point, one byte per axis
   static constexpr int kXBytes = ((NDIM * PGN_NCODES * 8 + 255) / 256) * 256;
   static constexpr int kWarpBytes = ((kXBytes + (64 + 3 * NDIM) * 8 + 255) / 256) * 256;
-  static constexpr int kMiscDoubles = 2 * PGN_NSETS * PGN_NRULES + 2 * PGN_NCODES;
+  static constexpr int kMiscDoubles = 3 * PGN_NSETS * PGN_NRULES + 2 * PGN_NCODES;  // scale, norm, weights; tp, tm
   static constexpr int kCodesOffset = kWarpsPerBlock * kWarpBytes + kMiscDoubles * 8;
   // the code table is padded to whole trips of 64 points (the padding holds the centre point's code)
   static constexpr int kPaddedPoints = ((feval_of(NDIM) + 63) / 64) * 64;
@@ -758,6 +775,7 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
   double* s_norm = s_scale + PGN_NSETS * PGN_NRULES;
   double* s_tp = s_norm + PGN_NSETS * PGN_NRULES;
   double* s_tm = s_tp + PGN_NCODES;
+  double* s_wc = s_tm + PGN_NCODES;  // [9][5] rule weights (EvalTuning<F>::kLaneWeightsSmem)
   uint32_t* s_codes = reinterpret_cast<uint32_t*>(sm + ((L::kCodesOffset + 15) / 16) * 16);
   unsigned char* s_set = reinterpret_cast<unsigned char*>(s_codes + L::kPaddedPoints * L::kCodeWords);
 
@@ -765,6 +783,7 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
   for (int i = threadIdx.x; i < PGN_NSETS * PGN_NRULES; i += blockDim.x) {
     s_scale[i] = __ldg(&P.scale[i]);
     s_norm[i] = __ldg(&P.norm[i]);
+    s_wc[i] = P.wc[i];
   }
   if (threadIdx.x < PGN_NCODES) {
     s_tp[threadIdx.x] = P.half_plus_g[threadIdx.x];
@@ -900,7 +919,10 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
       int set = P.half_set[q >> 5];
       if (set == 0xFF)
         set = lds_u8(set_addr + static_cast<uint32_t>(p < kFeval ? p : 0));
-      return P.wc + set * PGN_NRULES;
+      if constexpr (eval_lane_weights_smem<F>::value)
+        return static_cast<const double*>(s_wc) + set * PGN_NRULES;
+      else
+        return P.wc + set * PGN_NRULES;
     };
     // a trip whose points may belong to different generator sets and may not all exist (first, last)
     auto ragged_trip = [&](const double (&x)[2][NDIM], int t, bool keep_f) {

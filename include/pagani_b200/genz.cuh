@@ -426,6 +426,8 @@ struct EvalTuning<genz::Oscillatory<N>> {
   // 4 resident blocks (128 registers): every cosine literal stays in a register across the trip loop (5 of the 17 are
   // re-loaded per trip at 5 blocks): 2.81e11 vs 2.78e11 evaluations/s (profiles/r02_evalbench_j.jsonl, session G alike)
   static constexpr int kMinBlocks = 4;
+  // per-lane rule weights from shared memory: +1.1 % at 8-D, neutral at 5-D (profiles/r02_evalbench_s.jsonl)
+  static constexpr bool kLaneWeightsSmem = true;
 };
 template <int N>
 struct EvalTuning<genz::ProductPeak<N>> {
