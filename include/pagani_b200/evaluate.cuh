@@ -94,6 +94,17 @@ constexpr int kWarpsPerBlock = PGN_EVAL_WARPS;
 #ifndef PGN_EVAL_LANE_WEIGHTS_SMEM
 #define PGN_EVAL_LANE_WEIGHTS_SMEM 0
 #endif
+#ifndef PGN_EVAL_UNIT_JACOBIAN
+#define PGN_EVAL_UNIT_JACOBIAN 0
+#endif
+// warp index as a broadcast from lane 0 (warp-uniform for the compiler)
+#ifndef PGN_EVAL_UNIFORM_WARP
+#define PGN_EVAL_UNIFORM_WARP 1
+#endif
+// kernel instantiation without the integrand's range checks where the functor promises them (fast_in_box)
+#ifndef PGN_EVAL_NOCHECK
+#define PGN_EVAL_NOCHECK 1
+#endif
 
 // Launch-bound tuning knob of the evaluation kernel: resident 128-thread blocks per SM the register
 // allocation must allow (4 -> up to 128 registers per thread, 7 -> 72, 8 -> 64).  Cheap integrands
@@ -111,6 +122,19 @@ struct eval_segments : std::integral_constant<bool, PGN_EVAL_SEGMENTS != 0> {};
 template <typename F>
 struct eval_segments<F, std::void_t<decltype(EvalTuning<F>::kSegments)>>
   : std::integral_constant<bool, EvalTuning<F>::kSegments> {};
+// kUnitJacobianVariant: a second instantiation of the kernel for a unit Jacobian (integration over the unit cube),
+// without the multiplication of every function value by it (f * 1.0 = f exactly) and the load of the factor
+template <typename F, class = void>
+struct eval_unit_jacobian_variant : std::integral_constant<bool, PGN_EVAL_UNIT_JACOBIAN != 0> {};
+template <typename F>
+struct eval_unit_jacobian_variant<F, std::void_t<decltype(EvalTuning<F>::kUnitJacobianVariant)>>
+  : std::integral_constant<bool, EvalTuning<F>::kUnitJacobianVariant> {};
+// likewise kUniformWarp
+template <typename F, class = void>
+struct eval_uniform_warp : std::integral_constant<bool, PGN_EVAL_UNIFORM_WARP != 0> {};
+template <typename F>
+struct eval_uniform_warp<F, std::void_t<decltype(EvalTuning<F>::kUniformWarp)>>
+  : std::integral_constant<bool, EvalTuning<F>::kUniformWarp> {};
 // likewise kLaneWeightsSmem
 template <typename F, class = void>
 struct eval_lane_weights_smem : std::integral_constant<bool, PGN_EVAL_LANE_WEIGHTS_SMEM != 0> {};
@@ -188,6 +212,20 @@ template <class F, int N, int M>
 struct has_batch_fast<F, N, M,
                       std::void_t<decltype(std::declval<const F&>().template batch_fast<M>(
                         std::declval<const double (&)[M][N]>(), std::declval<double (&)[M]>()))>>
+  : std::true_type {};
+
+// Optional launch-time promise on top of batch_fast: `bool fast_in_box(const double* lo, const double* hi) const`
+// (host) says that every point of the integration volume takes batch_fast's fast path (its arguments are in range
+// whatever the region), and `batch_nocheck<M>(x, f)` is batch_fast without the per-point range checks (the same
+// values).  The launcher then picks a kernel instantiation without the checks, the vote and the fallback.
+template <class F, int N, int M, class = void>
+struct has_batch_nocheck : std::false_type {};
+template <class F, int N, int M>
+struct has_batch_nocheck<F, N, M,
+                         std::void_t<decltype(std::declval<const F&>().template batch_nocheck<M>(
+                                       std::declval<const double (&)[M][N]>(), std::declval<double (&)[M]>())),
+                                     decltype(std::declval<const F&>().fast_in_box(
+                                       std::declval<const double*>(), std::declval<const double*>()))>>
   : std::true_type {};
 
 struct EvalParams {
@@ -272,6 +310,45 @@ feval_of(int n)
   return 1 + 8 * n + 6 * n * (n - 1) + 4 * n * (n - 1) * (n - 2) / 3 + (1 << n);
 }
 
+// 64-bit shuffles as two 32-bit ones, LOW word first (the toolkit's double overloads shuffle the high word first):
+// the two results then land in an aligned register pair in issue order
+#ifndef PGN_EVAL_SHFL_LO_FIRST
+#define PGN_EVAL_SHFL_LO_FIRST 1
+#endif
+__device__ __forceinline__ double
+shfl_xor_f64(double v, int mask, int width = 32)
+{
+#if PGN_EVAL_SHFL_LO_FIRST
+  const int lo = __shfl_xor_sync(0xffffffffu, __double2loint(v), mask, width);
+  const int hi = __shfl_xor_sync(0xffffffffu, __double2hiint(v), mask, width);
+  return __hiloint2double(hi, lo);
+#else
+  return __shfl_xor_sync(0xffffffffu, v, mask, width);
+#endif
+}
+__device__ __forceinline__ double
+shfl_down_f64(double v, unsigned delta, int width = 32)
+{
+#if PGN_EVAL_SHFL_LO_FIRST
+  const int lo = __shfl_down_sync(0xffffffffu, __double2loint(v), delta, width);
+  const int hi = __shfl_down_sync(0xffffffffu, __double2hiint(v), delta, width);
+  return __hiloint2double(hi, lo);
+#else
+  return __shfl_down_sync(0xffffffffu, v, delta, width);
+#endif
+}
+__device__ __forceinline__ double
+shfl_idx_f64(double v, int src, int width = 32)
+{
+#if PGN_EVAL_SHFL_LO_FIRST
+  const int lo = __shfl_sync(0xffffffffu, __double2loint(v), src, width);
+  const int hi = __shfl_sync(0xffffffffu, __double2hiint(v), src, width);
+  return __hiloint2double(hi, lo);
+#else
+  return __shfl_sync(0xffffffffu, v, src, width);
+#endif
+}
+
 // first-wins arg-max over lanes (value v >= 0, index idx); ties go to the smaller index
 template <int WIDTH>
 __device__ __forceinline__ void
@@ -279,7 +356,7 @@ warp_argmax_first(double& v, int& idx)
 {
 #pragma unroll
   for (int off = WIDTH / 2; off > 0; off >>= 1) {
-    const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+    const double ov = shfl_xor_f64(v, off);
     const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
     if (ov > v || (ov == v && oi < idx)) {
       v = ov;
@@ -395,13 +472,13 @@ region_epilogue(const EvalParams& P, size_t reg, int lane, const double* s_f, co
   for (int r = 0; r < PGN_NRULES; ++r) {
     const double keep = lo_half ? sa[r] : sb[r];
     const double send = lo_half ? sb[r] : sa[r];
-    const double recv = __shfl_xor_sync(0xffffffffu, send, 16);
+    const double recv = shfl_xor_f64(send, 16);
     double v = __dadd_rn(keep, recv);  // lanes 0-15: A[i]+A[i+16]; lanes 16-31: B[i]+B[i+16]
-    v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, 8, 16));
-    v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, 4, 16));
-    v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, 2, 16));
-    v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, 1, 16));
-    tot[r] = __dadd_rn(__shfl_sync(0xffffffffu, v, 0), __shfl_sync(0xffffffffu, v, 16));
+    v = __dadd_rn(v, shfl_down_f64(v, 8, 16));
+    v = __dadd_rn(v, shfl_down_f64(v, 4, 16));
+    v = __dadd_rn(v, shfl_down_f64(v, 2, 16));
+    v = __dadd_rn(v, shfl_down_f64(v, 1, 16));
+    tot[r] = __dadd_rn(shfl_idx_f64(v, 0), shfl_idx_f64(v, 16));
   }
   // null-rule error (Sample.cuh:261-289): lane = 3*set + (rule-1)
   double term = 0.0;
@@ -414,16 +491,16 @@ region_epilogue(const EvalParams& P, size_t reg, int lane, const double* s_f, co
                      s_norm[s * PGN_NRULES + k + 1]);
     term = fmax(0.0, term);
   }
-  term = fmax(term, __shfl_down_sync(0xffffffffu, term, 12));
-  term = fmax(term, __shfl_down_sync(0xffffffffu, term, 6));
+  term = fmax(term, shfl_down_f64(term, 12));
+  term = fmax(term, shfl_down_f64(term, 6));
   {
-    const double t3 = __shfl_down_sync(0xffffffffu, term, 3);
-    const double t6 = __shfl_down_sync(0xffffffffu, term, 6);
+    const double t3 = shfl_down_f64(term, 3);
+    const double t6 = shfl_down_f64(term, 6);
     term = fmax(fmax(term, t3), t6);
   }
-  const double e1 = __shfl_sync(0xffffffffu, term, 0);
-  const double e2 = __shfl_sync(0xffffffffu, term, 1);
-  const double e3 = __shfl_sync(0xffffffffu, term, 2);
+  const double e1 = shfl_idx_f64(term, 0);
+  const double e2 = shfl_idx_f64(term, 1);
+  const double e3 = shfl_idx_f64(term, 2);
   if (lane == 0) {
     const bool benign = (__dmul_rn(5.0, e1) <= e2) && (__dmul_rn(5.0, e2) <= e3);
     const double inner = benign ? e1 : __dmul_rn(5.0, fmax(fmax(e1, e2), e3));
@@ -759,7 +836,9 @@ evaluate_region_exact(F* fptr, const EvalParams& P, size_t reg, int lane, uint32
 //     weights are then read from the kernel's constant parameter bank with a warp-uniform index
 //     (no LSU traffic); only the few half-chunks that straddle a set boundary look the set up per
 //     lane.
-template <typename F, int NDIM, bool BY_VALUE>
+// VAR: bit 0 = unit Jacobian (no f * 1.0), bit 1 = the functor's arguments are in range over the whole volume
+// (batch_nocheck instead of batch_fast: no range checks, no vote, no fallback)
+template <typename F, int NDIM, bool BY_VALUE, int VAR = 0>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, EvalTuning<F>::kMinBlocks)
 evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const __grid_constant__ EvalParams P)
 {
@@ -806,7 +885,14 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  // a broadcast from lane 0 is warp-uniform for the compiler's divergence analysis: the region index, the loop over
+  // the regions and the warp's shared-memory addresses move to the uniform datapath, and the shuffles of the epilogue
+  // are known to be convergent (no divergent twin of every shuffle group, no register moves where the twins rejoin:
+  // the kernel shrinks from 2190 to 1290 instructions).  +4 % F_1_8D, +9 % F_1_5D, +8 % F_3_8D, +2..4 % for the 10-D
+  // families and F_2_6D, -1.7 % F_4_8D (profiles/r02_evalbench_aa.jsonl): per-functor opt-out kUniformWarp.
+  int warp = threadIdx.x >> 5;
+  if constexpr (eval_uniform_warp<F>::value)
+    warp = __shfl_sync(0xffffffffu, warp, 0);
   unsigned char* warp_area = sm + warp * L::kWarpBytes;
   const uint32_t xbase = sm_addr + warp * L::kWarpBytes;  // 256-aligned
   double* s_x = reinterpret_cast<double*>(warp_area);
@@ -831,7 +917,9 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
   // by predication.
   constexpr int kTrips = (kFeval + 63) / 64;
   constexpr int kMiddle = kTrips >= 2 ? kTrips - 2 : 0;       // trips 1 .. kTrips-2: all 64 points exist
-  constexpr bool kFast = has_batch_fast<F, NDIM, 2>::value;   // straight-line values + exact fallback per region
+  constexpr bool UNIT_JAC = (VAR & 1) != 0;
+  constexpr bool kNoCheck = (VAR & 2) != 0;                   // straight-line values, in range by the functor's promise
+  constexpr bool kFast = !kNoCheck && has_batch_fast<F, NDIM, 2>::value;  // ... + exact fallback per region
   const double jac = P.jacobian;
   const double ratio = P.ratio;
   const double one_minus_ratio = __dsub_rn(1.0, ratio);
@@ -900,12 +988,19 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
     // f(x) * Jacobian of both points
     auto values = [&](const double (&x)[2][NDIM], double (&f)[2]) {
       double fv[2];
-      if constexpr (kFast)
+      if constexpr (kNoCheck)
+        static_cast<const F*>(fptr)->template batch_nocheck<2>(x, fv);
+      else if constexpr (kFast)
         exact = static_cast<const F*>(fptr)->template batch_fast<2>(x, fv) && exact;
       else
         BatchCall<F, NDIM, 2>::run(fptr, x, fv);
-      f[0] = __dmul_rn(fv[0], jac);
-      f[1] = __dmul_rn(fv[1], jac);
+      if constexpr (UNIT_JAC) {
+        f[0] = fv[0];
+        f[1] = fv[1];
+      } else {
+        f[0] = __dmul_rn(fv[0], jac);
+        f[1] = __dmul_rn(fv[1], jac);
+      }
     };
     auto accumulate = [&](double (&sum)[PGN_NRULES], double fun, const double* w) {
       sum[0] = __fma_rn(fun, w[0], sum[0]);
@@ -1032,13 +1127,15 @@ evaluate_kernel_bp(const __grid_constant__ FunctorArg<F, BY_VALUE> farg, const _
           // none of the points 64 (kTrips-1) + 32 + lane exists: chain B is complete, only chain A has a last term
           double xa[1][NDIM], fv[1];
           gather_a(xa[0], kTrips - 1);
-          if constexpr (has_batch_fast<F, NDIM, 1>::value)
+          if constexpr (kNoCheck)
+            static_cast<const F*>(fptr)->template batch_nocheck<1>(xa, fv);
+          else if constexpr (has_batch_fast<F, NDIM, 1>::value)
             exact = static_cast<const F*>(fptr)->template batch_fast<1>(xa, fv) && exact;
           else
             BatchCall<F, NDIM, 1>::run(fptr, xa, fv);
           const int pa = ((kTrips - 1) << 6) + lane;
           if (pa < kFeval)
-            accumulate(sa, __dmul_rn(fv[0], jac), lane_weights((kTrips - 1) << 6, pa));
+            accumulate(sa, UNIT_JAC ? fv[0] : __dmul_rn(fv[0], jac), lane_weights((kTrips - 1) << 6, pa));
         } else {
           gather(x, kTrips - 1);
           ragged_trip(x, kTrips - 1, false);
@@ -1081,7 +1178,7 @@ launch_evaluate(F* functor, const pgn_region_view* v)
     return PGN_ERR_INVALID;
   if (v->n == 0)
     return PGN_OK;
-  EvalParams P;
+  EvalParams P{};
   P.left = v->left;
   P.length = v->length;
   P.n = v->n;
@@ -1180,8 +1277,30 @@ launch_evaluate(F* functor, const pgn_region_view* v)
 
   constexpr bool kCodesFit = smem_bytes<NDIM>(true) <= 100 * 1024;
   if constexpr (NDIM <= 12) {
-    if (v->reserved != kVariantShift)
+    if (v->reserved != kVariantShift) {
+      if constexpr (eval_unit_jacobian_variant<F>::value) {
+        if (v->jacobian == 1.0) {
+          if constexpr (PGN_EVAL_NOCHECK != 0 && has_batch_nocheck<F, NDIM, 2>::value) {
+            // the functor's promise for the whole integration volume (every region lies inside it)
+            double lo[NDIM], hi[NDIM];
+            for (int d = 0; d < NDIM; ++d) {
+              lo[d] = v->lows[d];
+              hi[d] = v->lows[d] + v->ranges[d];
+            }
+            bool in_range = false;
+            if constexpr (std::is_default_constructible<F>::value) {
+              in_range = functor != nullptr ? functor->fast_in_box(lo, hi) : F{}.fast_in_box(lo, hi);
+            } else {
+              in_range = functor != nullptr && functor->fast_in_box(lo, hi);
+            }
+            if (in_range)
+              return launch(KernelTag<evaluate_kernel_bp<F, NDIM, kByValue, 3>>{}, BpLayout<NDIM>::bytes());
+          }
+          return launch(KernelTag<evaluate_kernel_bp<F, NDIM, kByValue, 1>>{}, BpLayout<NDIM>::bytes());
+        }
+      }
       return launch(KernelTag<evaluate_kernel_bp<F, NDIM, kByValue>>{}, BpLayout<NDIM>::bytes());
+    }
   }
   return launch(KernelTag<evaluate_kernel<F, NDIM, kByValue, kCodesFit>>{}, smem_bytes<NDIM>(kCodesFit));
 }

@@ -123,6 +123,31 @@ struct Oscillatory {
     }
     return ok;
   }
+  // launch-time promise (evaluate.cuh: has_batch_nocheck): over the box [lo, hi] the cosine's argument stays far
+  // inside the fast path's range |s| < 2^31 (the bound leaves room for the rounding of the sum)
+  PGN_HD bool
+  fast_in_box(const double* lo, const double* hi) const
+  {
+    double bound = 0.;
+    for (int k = 0; k < N; ++k) {
+      const double a = lo[k] < 0. ? -lo[k] : lo[k], b = hi[k] < 0. ? -hi[k] : hi[k];
+      bound += static_cast<double>(k + 1) * (a > b ? a : b);
+    }
+    return bound < 1073741824.;  // false for NaN bounds as well
+  }
+  template <int M>
+  __device__ void
+  batch_nocheck(const double (&x)[M][N], double (&f)[M]) const
+  {
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      double s = x[m][0];
+#pragma unroll
+      for (int k = 1; k < N; ++k)
+        s = s + static_cast<double>(k + 1) * x[m][k];
+      f[m] = ::pagani_b200::fastmath::cos_in_range(s);
+    }
+  }
 #endif
 };
 
@@ -277,6 +302,8 @@ struct CZero {
     }
     return ok;
   }
+  // (a batch_nocheck form without the range test of exp -- two integer instructions per point -- measured 0.5-1.5 %
+  // SLOWER at 10-D, profiles/r02_evalbench_ab.jsonl: not offered)
 #endif
 };
 
@@ -423,11 +450,16 @@ struct EvalTuning;
 #ifndef PGN_EVAL_NO_GENZ_TUNING  // tools/evalbench sweeps the knob through the primary template instead
 template <int N>
 struct EvalTuning<genz::Oscillatory<N>> {
-  // 4 resident blocks (128 registers): every cosine literal stays in a register across the trip loop (5 of the 17 are
-  // re-loaded per trip at 5 blocks): 2.81e11 vs 2.78e11 evaluations/s (profiles/r02_evalbench_j.jsonl, session G alike)
-  static constexpr int kMinBlocks = 4;
+  // launch bound 5 (at most 102 registers; the unit-cube kernel takes 80, six resident blocks).  With the
+  // warp-uniform warp index of evaluate.cuh the cosine literals live in uniform registers whatever the bound, and the
+  // smaller allocation wins: 3.007e11 vs 2.98e11 evaluations/s at a bound of 4 (profiles/r02_evalbench_z.jsonl;
+  // before that change 4 was ahead, r02_evalbench_j.jsonl)
+  static constexpr int kMinBlocks = 5;
   // per-lane rule weights from shared memory: +1.1 % at 8-D, neutral at 5-D (profiles/r02_evalbench_s.jsonl)
   static constexpr bool kLaneWeightsSmem = true;
+  // second kernel instantiation for the unit cube, without f * 1.0: +1.6 % (profiles/r02_evalbench_u.jsonl); a third
+  // one without the |s| < 2^31 checks when fast_in_box() promises them for the whole volume: +2.7 % (r02_evalbench_v)
+  static constexpr bool kUnitJacobianVariant = true;
 };
 template <int N>
 struct EvalTuning<genz::ProductPeak<N>> {
@@ -437,6 +469,14 @@ template <int N>
 struct EvalTuning<genz::CZero<N>> {
   static constexpr int kMinBlocks = 4;     // the primary template's default
   static constexpr bool kSegments = true;  // +4 % at 10-D (r02_evalbench_h.jsonl)
+  // unit-cube kernel without f * 1.0: +3.8 % at 10-D together with the warp-uniform warp index (-5 % without it;
+  // profiles/r02_evalbench_aa.jsonl)
+  static constexpr bool kUnitJacobianVariant = true;
+};
+template <int N>
+struct EvalTuning<genz::Discontinuous<N>> {
+  static constexpr int kMinBlocks = 4;
+  static constexpr bool kUnitJacobianVariant = true;  // +0.7 % at 10-D (profiles/r02_evalbench_aa.jsonl)
 };
 template <int N>
 struct EvalTuning<genz::CornerPeak<N>> {
@@ -445,6 +485,8 @@ struct EvalTuning<genz::CornerPeak<N>> {
 template <int N>
 struct EvalTuning<genz::Gaussian<N>> {
   static constexpr int kMinBlocks = PGN_GENZ_FAST_POW ? 3 : 8;
+  // warp-uniform warp index: +1.4 % at 5-D, -1.7 % at 8-D (profiles/r02_evalbench_aa.jsonl)
+  static constexpr bool kUniformWarp = N < 8;
 };
 #endif
 }  // namespace pagani_b200
