@@ -481,6 +481,22 @@ def main():
                 f"{ncu.get('regions')} regions, {ncu['dram_bytes_per_region']:.1f} B per region for 16*ndim+20 = "
                 f"{16 * NDIM + 20} algorithmic bytes) x regions of the average launch of this run")
         out["roofline"]["ncu_source"] = ncu.get("source")
+        # The bound this kernel actually runs against: every warp instruction takes one issue cycle of
+        # its scheduler and an FP64 instruction a second one; instruction mix from the same ncu capture, SM clock
+        # from the samples of this run.
+        try:
+            sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+            mhz = (clocks or {}).get("sm_mhz")
+            wi, fi = ncu.get("warp_instructions_per_evaluation"), ncu.get("fp64_instructions_per_evaluation")
+            if sms and mhz and wi and fi:
+                bound = sms * 4 * mhz * 1e6 * 32.0 / (wi + fi)
+                out["roofline"]["issue_bound"] = {
+                    "issue_cycles_per_32_evals": wi + fi, "evals_per_s": bound,
+                    "frac": out["roofline"]["kernel_evals_per_s"] / bound,
+                    "note": f"{sms} SMs x 4 schedulers x {mhz:g} MHz x 32 evaluations / ({wi:.1f} warp instructions + "
+                            f"{fi:.1f} second cycles of FP64 instructions per 32 evaluations)"}
+        except Exception:  # a reporting extra must never cost the bench line
+            pass
     if not args.no_side_legs and world == 1:
         # HBM-bound stages at the largest iteration: classify 29 B/region, fused compact+split (48 ndim + 36) B
         # per surviving region, measured peak from MEASURED_PEAKS.json (driver-written copy bandwidth)

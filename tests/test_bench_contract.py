@@ -78,6 +78,7 @@ def bench(monkeypatch):
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
     monkeypatch.setattr(torch.cuda, "ExternalStream", lambda ptr, device=None: object())
     monkeypatch.setattr(torch.cuda, "Event", _Event)
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda d: types.SimpleNamespace(multi_processor_count=148))
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
     monkeypatch.setattr(pg, "Workspace", _Workspace)
     monkeypatch.setattr(pg, "Genz", lambda f, n: types.SimpleNamespace(flops_per_eval=107.0, true_value=3.44e-05, name="F_1_8D"))
@@ -102,6 +103,13 @@ CONTRACT = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step
 
 def test_bench_line_carries_every_contract_key(bench, monkeypatch):
     monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "2", "--warmup", "1"])
+    real_stop = bench.ClockSampler.stop
+
+    def stop(self):  # no nvidia-smi in the CPU container: keep the sampler's shutdown, supply the clocks
+        real_stop(self)
+        return {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": [], "samples": 3}
+
+    monkeypatch.setattr(bench.ClockSampler, "stop", stop)
     buf = io.StringIO()
     with redirect_stdout(buf):
         bench.main()
@@ -135,6 +143,9 @@ def test_bench_line_carries_every_contract_key(bench, monkeypatch):
     assert [c["family"] for c in d["configs"]] == [2, 5, 6, 4] and all("parity" in c and "ours" in c for c in d["configs"])
     assert d["native_ladder"]["steps"] and d["native_ladder"]["steps"][0]["epsrel"] == 1e-3
     assert d["roofline"]["fp64_pipe_pct"] > 0 and d["roofline"]["frac_executed"] > 0
+    ib = d["roofline"]["issue_bound"]  # from the committed ncu instruction mix and the sampled SM clock
+    assert ib["evals_per_s"] == pytest.approx(148 * 4 * 1965e6 * 32 / ib["issue_cycles_per_32_evals"])
+    assert ib["frac"] == pytest.approx(d["roofline"]["kernel_evals_per_s"] / ib["evals_per_s"])
     hbm = d["roofline_hbm"]
     assert "error" not in hbm and hbm["regions"] == 1024 and hbm["largest_all_active_iteration"]["regions"] == 512
 
