@@ -218,6 +218,9 @@ struct has_batch_fast<F, N, M,
 // (host) says that every point of the integration volume takes batch_fast's fast path (its arguments are in range
 // whatever the region), and `batch_nocheck<M>(x, f)` is batch_fast without the per-point range checks (the same
 // values).  The launcher then picks a kernel instantiation without the checks, the vote and the fallback.
+// The promise is asked for the integration VOLUME: it covers every region because regions are expressed in unit-cube
+// coordinates, the invariant of the reference's region store (Sub_regions.cuh:11-36); a caller that imports regions
+// outside [0, 1]^ndim must not offer it (fast_in_box should then answer for the box those regions map to).
 template <class F, int N, int M, class = void>
 struct has_batch_nocheck : std::false_type {};
 template <class F, int N, int M>
